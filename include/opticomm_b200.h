@@ -1,0 +1,204 @@
+/*
+ * opticomm_b200.h — C-ABI of the B200-native (sm_100a) hot path for OptiCommPy.
+ *
+ * Drop-in boundary.  The reference has no FFI: its boundary is a set of
+ * Python call signatures taking numpy arrays + a `parameters` attribute bag.  Each entry
+ * point below is what a ctypes binding for one of those calls binds to; the citation is
+ * the reference function it replaces (paths relative to the OptiCommPy v0.11.0 tree).
+ *
+ * Conventions
+ *   - plain C types only; `void*` device pointers are owned by the caller (torch tensors
+ *     used as device-memory containers); `stream` is a cudaStream_t passed as void*.
+ *   - every call returns 0 on success, non-zero otherwise; ocb_last_error() returns a
+ *     thread-local message for the last failure.
+ *   - complex64 samples are (re, im) float pairs; complex128 are (re, im) double pairs.
+ *   - field layout inside the library is PLANAR: rows[2K][N]; row p (p<K) is the x-pol of
+ *     pol-pair p, row K+p its y-pol (reference: Ei[:, 0::2].T / Ei[:, 1::2].T,
+ *     optic/models/channels.py:364-365).
+ *   - "_host" variants take HOST pointers and perform H2D / D2H themselves (this is the
+ *     call the end-to-end number in bench.py goes through).
+ */
+#ifndef OPTICOMM_B200_H
+#define OPTICOMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCB_ABI_VERSION 1
+
+/* dtype tags for host/device sample buffers */
+#define OCB_C64 0  /* complex64  */
+#define OCB_C128 1 /* complex128 */
+
+/* amplifier modes (optic/models/channels.py:443-451, optic/dsp/equalization.py:1090-1095) */
+#define OCB_AMP_NONE 0
+#define OCB_AMP_IDEAL 1
+#define OCB_AMP_EDFA 2
+
+/* noise source for OCB_AMP_EDFA */
+#define OCB_NOISE_INJECTED 0 /* caller supplies one (rows_per_pol, N) complex64 buffer that is
+                                added to x and y of every span — exactly what the reference CPU
+                                path does when param.seed is set (channels.py:356, 443-445) */
+#define OCB_NOISE_PHILOX 1   /* on-device Philox4x32-10 + Box-Muller, independent per pol/span */
+
+/* equalizer algorithms (optic/dsp/equalization.py:477-510) */
+#define OCB_ALG_CMA 0
+#define OCB_ALG_RDE 1
+#define OCB_ALG_NLMS 2
+#define OCB_ALG_DDLMS 3
+#define OCB_ALG_DARDE 4
+#define OCB_ALG_STATIC 5
+
+typedef struct ocb_ssfm_plan ocb_ssfm_plan; /* opaque: cuFFT plans + workspace partition */
+
+/* ---- library ------------------------------------------------------------------------ */
+int ocb_abi_version(void);
+const char* ocb_last_error(void);
+/* Number of kernels launched by this library in the calling thread since the last reset
+ * (bench.py's "gpu_launches" claim is read from here). */
+int64_t ocb_launch_count(void);
+void ocb_launch_count_reset(void);
+
+/* ---- SSFM plan lifecycle -------------------------------------------------------------
+ * One plan per (device, N, rows).  rows = 2K for manakovSSF/manakovDBP, 1 for ssfm.
+ * The plan owns cuFFT handles; all device memory is a caller-provided workspace.       */
+int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out);
+int64_t ocb_ssfm_plan_workspace_bytes(const ocb_ssfm_plan* plan);
+int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* plan, void* dev_ptr, int64_t bytes);
+int ocb_ssfm_plan_destroy(ocb_ssfm_plan* plan);
+
+/* ---- layout conversion ---------------------------------------------------------------
+ * (N, C) interleaved-column host/device array <-> planar rows[C][N] complex64.
+ * column 2p -> row p, column 2p+1 -> row C/2+p when pairs != 0; identity order otherwise.
+ * Replaces: Ei[:, 0::2].T / Ech[:, 0::2] = Ech_x.T (channels.py:364-365, 461-463).      */
+int ocb_pack_fields(const void* src_dev, int src_dtype, int64_t N, int C, int pairs,
+                    void* rows_dev, void* stream);
+int ocb_unpack_fields(const void* rows_dev, int64_t N, int C, int pairs, void* dst_dev,
+                      int dst_dtype, void* stream);
+
+/* ---- Manakov SSFM / DBP ---------------------------------------------------------------
+ * Replaces optic.models.channels.manakovSSF (channels.py:252-468; direction=+1) and
+ * optic.dsp.equalization.manakovDBP (equalization.py:976-1173; direction=-1).          */
+typedef struct ocb_manakov_params {
+    double alpha_lin;        /* α [1/km]  = alpha_dB/(10 log10 e)      channels.py:346 */
+    double beta2;            /* β2 [s^2/km]                            channels.py:347 */
+    double gamma;            /* γ [1/W/km]                             channels.py:348 */
+    double Fs;               /* sampling rate [Hz]                                     */
+    double Lspan;            /* span length [km]                                       */
+    double hz;               /* fixed step [km]                        channels.py:398-403 */
+    double maxNlinPhaseRot;  /* adaptive-step phase budget [rad]       channels.py:392-397 */
+    double tol;              /* fixed-point tolerance                  channels.py:429 */
+    int32_t n_spans;
+    int32_t maxIter;
+    int32_t nlprMethod;      /* 1 = adaptive step */
+    int32_t direction;       /* +1 forward (SSF), -1 backward (DBP) */
+    int32_t amp_mode;        /* OCB_AMP_* */
+    int32_t noise_mode;      /* OCB_NOISE_* (only for OCB_AMP_EDFA, forward) */
+    double edfa_gain_lin;    /* G_lin = 10^(alpha*Lspan/10)            devices.py:713 */
+    double edfa_noise_var;   /* p_noise = N_ase*Fs                     devices.py:721-722 */
+    uint64_t seed;           /* Philox key */
+    int32_t n_save;          /* number of span snapshots requested (0 = final field only) */
+    int32_t reserved;
+} ocb_manakov_params;
+
+typedef struct ocb_manakov_stats {
+    int64_t steps;         /* executed SSFM loop steps over all spans (channels.py:387) */
+    int64_t iterations;    /* executed fixed-point iterations over all steps (channels.py:413) */
+    int64_t nonconverged;  /* steps that hit maxIter without lim < tol (channels.py:431-434) */
+    double last_lim;
+    double z_last_step;    /* size of the last executed step [km] */
+} ocb_manakov_stats;
+
+/* rows_inout: planar (2K, N) complex64, propagated in place.
+ * noise_dev : (K, N) complex64 or NULL (OCB_NOISE_INJECTED only).
+ * save_spans: n_save ascending 1-based span indices or NULL; snapshots are written to
+ *             save_dev as n_save consecutive planar (2K, N) blocks (channels.py:453-456). */
+int ocb_manakov_run(ocb_ssfm_plan* plan, void* rows_inout, const ocb_manakov_params* prm,
+                    const void* noise_dev, const int32_t* save_spans, void* save_dev,
+                    ocb_manakov_stats* stats, void* stream);
+
+/* Host-buffer variant: Ei_host is the reference-layout (N, 2K) array (complex64/128), the
+ * result is written to Eo_host with the same layout and out_dtype (H2D, pack, run, unpack,
+ * D2H inside).  noise_host: (K, N) complex64 or NULL.  With n_save > 0, Eo_host receives n_save
+ * consecutive (N, 2K) blocks (one per snapshot); the Python shim interleaves them column-wise
+ * into the reference's (N, 2K*n_save) layout. */
+int ocb_manakov_run_host(ocb_ssfm_plan* plan, const void* Ei_host, int in_dtype, void* Eo_host,
+                         int out_dtype, const ocb_manakov_params* prm, const void* noise_host,
+                         const int32_t* save_spans, ocb_manakov_stats* stats, void* stream);
+
+/* One fixed-point pass of the nonlinear step on caller buffers (unit parity + ncu target).
+ * Replaces channels.py:414-417 (rotation) + :424 (convergence sums) + :436 (phase update):
+ *   out   = Ehd * exp(j*dir*hz*(8/9)γ(Pch + |Ec_x|^2 + |Ec_y|^2)/2)
+ *   sums  = { Σ|Efd-Ec|^2, Σ|Ec|^2, max(|Efd_x|^2+|Efd_y|^2) }   (3 doubles, device)
+ * All fields planar (2K, N) complex64; Pch (K, N) float32.  If Efd == NULL the pass is the
+ * first one of a step: Ec is the step-start field, Pch is WRITTEN (|Ec_x|^2+|Ec_y|^2).     */
+int ocb_manakov_nl_pass(const void* Ehd, const void* Efd, const void* Ec, void* Pch, void* out,
+                        void* sums3_dev, int64_t N, int K, double gamma, double hz, int direction,
+                        void* stream);
+
+/* ---- scalar NLSE SSFM -----------------------------------------------------------------
+ * Replaces optic.models.channels.ssfm (channels.py:112-249).  rows = 1 plan.            */
+typedef struct ocb_nlse_params {
+    double alpha_lin, beta2, gamma, Fs, hz;
+    int32_t n_spans, n_steps; /* Nspans, Nsteps = floor(Lspan/hz)   channels.py:205-206 */
+    int32_t amp_mode, noise_mode;
+    double edfa_gain_lin, edfa_noise_var;
+    uint64_t seed;
+} ocb_nlse_params;
+int ocb_nlse_run(ocb_ssfm_plan* plan, void* row_inout, const ocb_nlse_params* prm,
+                 const void* noise_dev, void* stream);
+int ocb_nlse_run_host(ocb_ssfm_plan* plan, const void* Ei_host, int in_dtype, void* Eo_host,
+                      int out_dtype, const ocb_nlse_params* prm, const void* noise_host,
+                      void* stream);
+
+/* ---- EDFA ------------------------------------------------------------------------------
+ * Replaces optic.models.devices.edfa (devices.py:671-726) on planar rows: E = E*sqrt(G)+n. */
+int ocb_edfa_apply(void* rows_inout, int rows, int64_t N, double gain_lin, double noise_var,
+                   int noise_mode, const void* noise_dev, int noise_rows, uint64_t seed,
+                   uint64_t stream_id, void* stream);
+
+/* ---- EDC (overlap-save CD compensation) -------------------------------------------------
+ * Replaces optic.dsp.equalization.edc (equalization.py:36-122) ->
+ * optic.dsp.core.blockwiseFFTConv(freqDomainFilter=True) (core.py:973-1046).
+ * h_taps: the K time-domain taps fftshift(ifft(H)) (host computes them in float64 and passes
+ * them as complex64 device array).  x: planar (nModes, L) complex64.  y: same shape.
+ * The result equals conv(x, h)[D : D+L], D=(K-1)//2 (core.py:1004, 1044).                */
+int64_t ocb_edc_workspace_bytes(int64_t L, int nModes, int K);
+int ocb_edc_run(const void* x_rows, void* y_rows, int64_t L, int nModes, const void* h_taps,
+                int K, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- N x N adaptive MIMO equalizer --------------------------------------------------------
+ * Replaces optic.dsp.equalization.coreAdaptEq (equalization.py:354-516) and the tap-update
+ * kernels cmaUp/rdeUp/nlmsUp/ddlmsUp/dardeUp (:520-973) for a batch of independent streams,
+ * one persistent warp per stream.  All strides are in ELEMENTS of the respective array, so a
+ * training stage is a pointer offset into the full buffers (equalization.py:276-293).
+ *   x      : stream s starts at x + s*x_stream_stride; (nSamp, nModes) complex64 samples available,
+ *            already zero-padded like equalization.py:227-231
+ *   ref    : stream s at ref + s*ref_stream_stride; (L, nModes) complex64 (NLMS / DA-RDE) or NULL
+ *   H, Hwl : (nStreams, nModes^2, nTaps) complex64, updated in place (Hwl NULL unless runWL)
+ *   y      : stream s at y + s*y_stream_stride; (L, nModes) complex64
+ *   errSq  : stream s, mode m at errSq + s*err_stream_stride + m*err_mode_stride; L float32
+ *   Hiter  : NULL, or (nStreams, L, nModes^2, nTaps) complex64 tap history (storeCoeff, :511-512)
+ *   constSymb (M) complex64 ; radii (nR) float32 ascending (np.unique(|c|), :456) ; Rcma (:453)  */
+int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hwl, void* y, void* errSq,
+                    void* Hiter, int nStreams, int64_t nSamp, int64_t x_stream_stride,
+                    int64_t ref_stream_stride, int64_t y_stream_stride, int64_t err_stream_stride,
+                    int64_t err_mode_stride, int64_t L, int nModes, int nTaps, int SpS, int alg,
+                    float mu, const void* constSymb, int M, const void* radii, int nR, float Rcma,
+                    int runWL, void* stream);
+
+/* ---- blind phase search ----------------------------------------------------------------------
+ * Replaces optic.dsp.carrierRecovery.bps (carrierRecovery.py:172-223).
+ *   x     : (L, nModes) complex128 (double pairs) device array, modes interleaved as in the reference
+ *   constSymb : (M) complex128 ; B test phases b*(pi/2)/B ; Nhalf = N of the 2N+1 window
+ *   idx_out : (L, nModes) int32 argmin index ; phase_out : (L, nModes) float64 = testPhases[idx] */
+int ocb_bps_run(const void* x, int64_t L, int nModes, const void* constSymb, int M, int B, int Nhalf,
+                void* idx_out, void* phase_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTICOMM_B200_H */

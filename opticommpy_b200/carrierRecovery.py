@@ -1,0 +1,140 @@
+"""Drop-in mirrors of ``optic.dsp.carrierRecovery.bps`` and the ``cpr`` wrapper around it.
+
+``bps`` (carrierRecovery.py:172-223) runs on the GPU through ``ocb_bps_run`` in float64, like the
+reference.  ``cpr`` (carrierRecovery.py:37-169) keeps the reference's parameter names, defaults
+and post-processing (4th-power FOE, ``unwrap(4φ)/4``, power normalisation); only ``alg='bps'``
+(and its alias ``'bpsGPU'``, the reference's own GPU selector) is part of this hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging as logg
+
+import numpy as np
+from numpy.fft import fft, fftfreq, fftshift
+
+from . import _cabi
+from .modulation import grayMapping
+
+_vp = C.c_void_p
+
+
+def _pnorm(x):
+    """Normalise the average power of ``x`` over all entries (optic/dsp/core.py:702-717)."""
+    return x / np.sqrt(np.mean(x * np.conj(x)).real)
+
+
+def bps(sigIn, N, constSymb, B, returnIndex=False):
+    """
+    Blind phase search (BPS) on the GPU.
+
+    Parameters
+    ----------
+    sigIn : (L, nModes) complex array of received symbols.
+    N : half-length of the 2N+1 averaging window.
+    constSymb : complex constellation.
+    B : number of test phases b*(pi/2)/B.
+    returnIndex : also return the int32 argmin indices (extension, default False).
+
+    Returns
+    -------
+    phaseEst : (L, nModes) float64, each entry one of the B test phases.
+    """
+    torch = _cabi.require_cuda()
+    lib = _cabi.lib()
+    x = np.ascontiguousarray(np.asarray(sigIn).astype(np.complex128))
+    if x.ndim != 2:
+        raise IndexError("bps expects a 2-D (symbols, modes) array")  # sigIn.shape[1], :197
+    L, nModes = x.shape
+    c = np.ascontiguousarray(np.asarray(constSymb).astype(np.complex128))
+    d_x = torch.from_numpy(x.view(np.float64)).to("cuda")
+    d_c = torch.from_numpy(c.view(np.float64)).to("cuda")
+    d_idx = torch.empty((L, nModes), dtype=torch.int32, device="cuda")
+    d_ph = torch.empty((L, nModes), dtype=torch.float64, device="cuda")
+    _cabi.check(
+        lib.ocb_bps_run(_vp(d_x.data_ptr()), L, nModes, _vp(d_c.data_ptr()), len(c), int(B), int(N),
+                        _vp(d_idx.data_ptr()), _vp(d_ph.data_ptr()), _vp(_cabi.stream_ptr(torch))),
+        "ocb_bps_run",
+    )
+    phaseEst = d_ph.cpu().numpy()
+    if returnIndex:
+        return phaseEst, d_idx.cpu().numpy()
+    return phaseEst
+
+
+def fourthPowerFOE(sigIn, Fs, M=4):
+    """4th-power frequency-offset estimate/compensation (carrierRecovery.py:333-371), host side."""
+    Nfft = sigIn.shape[0]
+    f = fftshift(Fs * fftfreq(Nfft))
+    nModes = sigIn.shape[1]
+    sigOut = sigIn.copy()
+    t = np.arange(0, sigOut.shape[0]) * 1 / Fs
+    fo = np.zeros(nModes)
+    for n in range(nModes):
+        spec = 10 * np.log10(np.abs(fftshift(fft(sigIn[:, n] ** M))))
+        fo[n] = f[np.argmax(spec)] / M
+        sigOut[:, n] = sigIn[:, n] * np.exp(-1j * 2 * np.pi * fo[n] * t)
+    return sigOut, fo
+
+
+def cpr(sigIn, param=None, symbTx=None):
+    """
+    Carrier phase recovery (CPR) with the BPS algorithm on the GPU.
+
+    Parameters as in the reference (carrierRecovery.py:48-58): alg ['bps'], M [4], constType
+    ['qam'], shapingFactor [0], B [64], N [35], Ts [1/32e9], runFOE [True], returnPhases [False].
+    Returns ``sigOut`` or ``(sigOut, phaseEst)``.
+    """
+    if param is None:
+        param = []
+    alg = getattr(param, "alg", "bps")
+    M = getattr(param, "M", 4)
+    constType = getattr(param, "constType", "qam")
+    shapingFactor = getattr(param, "shapingFactor", 0)
+    B = getattr(param, "B", 64)
+    N = getattr(param, "N", 35)
+    Ts = getattr(param, "Ts", 1 / 32e9)
+    runFOE = getattr(param, "runFOE", True)
+    returnPhases = getattr(param, "returnPhases", False)
+
+    sigIn = np.asarray(sigIn)
+    try:
+        sigIn.shape[1]
+        input1D = False
+    except IndexError:
+        sigIn = sigIn.reshape(len(sigIn), 1)
+        input1D = True
+
+    constSymb = grayMapping(M, constType)  # complex64, like the reference (:118-121)
+    px = np.exp(-shapingFactor * np.abs(constSymb) ** 2)
+    px = px / np.sum(px)
+    constSymb /= np.sqrt(np.sum(np.abs(constSymb) ** 2 * px))
+
+    if runFOE:  # :124-131
+        logg.info("Running frequency offset compensation...")
+        sigIn, fo = fourthPowerFOE(sigIn, 1 / Ts, M if constType in ["psk", "apsk"] else 4)
+        sigIn = _pnorm(sigIn)
+        logg.info(f"Estimated frequency offset (MHz): {np.round(fo / 1e6, 3)}")
+
+    if alg in ("bps", "bpsGPU"):
+        logg.info("Running BPS carrier phase recovery...")
+        phaseEst = bps(sigIn, N // 2, constSymb, B)  # :138
+    elif alg in ("ddpll", "viterbi"):
+        raise NotImplementedError(f"cpr alg '{alg}' is outside the B200 hot path (SURVEY.md §2 row 3)")
+    else:
+        logg.error("CPR algorithm incorrectly specified.")
+        raise NameError("name 'phaseEst' is not defined")  # the reference falls through to :154
+
+    phaseEst = np.unwrap(4 * phaseEst, axis=0) / 4  # :154
+
+    discard = phaseEst.shape[0] // 4
+    if discard > 0:
+        sigmaPhase = np.mean(np.var(np.diff(phaseEst[discard:-discard, :], axis=0), axis=0))
+        logg.info(f"Estimated linewidth: {sigmaPhase / (2 * np.pi * Ts) / 1e3:.3f} kHz")
+
+    sigOut = _pnorm(sigIn * np.exp(1j * phaseEst))  # :162
+
+    if input1D:
+        sigOut = sigOut.flatten()
+        phaseEst = phaseEst.flatten()
+    return (sigOut, phaseEst) if returnPhases else sigOut

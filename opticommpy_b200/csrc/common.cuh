@@ -1,0 +1,92 @@
+// Shared helpers for the sm_100a hot-path kernels: error plumbing, launch accounting,
+// vectorised complex64 access and warp/block reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace ocb {
+
+// ---- error state (thread-local, read through ocb_last_error) ---------------------------
+std::string& last_error();
+int fail(const char* what, const char* file, int line);
+int64_t& launch_counter();
+
+#define OCB_CUDA(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            char _b[512];                                                           \
+            snprintf(_b, sizeof _b, "%s -> %s", #expr, cudaGetErrorString(_e));     \
+            return ::ocb::fail(_b, __FILE__, __LINE__);                             \
+        }                                                                           \
+    } while (0)
+
+#define OCB_CUFFT(expr)                                                             \
+    do {                                                                            \
+        cufftResult _r = (expr);                                                    \
+        if (_r != CUFFT_SUCCESS) {                                                  \
+            char _b[512];                                                           \
+            snprintf(_b, sizeof _b, "%s -> cufft error %d", #expr, (int)_r);        \
+            return ::ocb::fail(_b, __FILE__, __LINE__);                             \
+        }                                                                           \
+    } while (0)
+
+#define OCB_REQUIRE(cond, msg)                                                      \
+    do {                                                                            \
+        if (!(cond)) return ::ocb::fail(msg, __FILE__, __LINE__);                   \
+    } while (0)
+
+// Every kernel launch of the library goes through this so that bench.py can report how many
+// of OUR kernels ran inside a timed region.
+#define OCB_LAUNCH(kernel, grid, block, smem, stream, ...)                          \
+    do {                                                                            \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
+        ::ocb::launch_counter()++;                                                  \
+        OCB_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+inline int grid_for(int64_t work_items, int block, int per_thread, int max_waves = 8) {
+    int64_t blocks = (work_items + (int64_t)block * per_thread - 1) / ((int64_t)block * per_thread);
+    int64_t cap = (int64_t)kNumSMs * max_waves;
+    if (blocks > cap) blocks = cap;  // grid-stride beyond this
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming 128-bit accesses (two complex64 per transaction)
+__device__ __forceinline__ float4 ldg4(const float2* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void stg4(float2* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+}  // namespace ocb

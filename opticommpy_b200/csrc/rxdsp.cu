@@ -1,0 +1,473 @@
+// Receiver-DSP kernels behind the C-ABI: EDC (overlap-save), N x N adaptive MIMO equalizer,
+// blind phase search.  Reference behaviour restated (not code):
+//   edc / blockwiseFFTConv : optic/dsp/equalization.py:36-122, optic/dsp/core.py:973-1046
+//   coreAdaptEq + *Up      : optic/dsp/equalization.py:354-516, 520-973
+//   bps                    : optic/dsp/carrierRecovery.py:172-223
+#include <math.h>
+
+#include "../../include/opticomm_b200.h"
+#include "common.cuh"
+
+using namespace ocb;
+
+// =============================================================================================
+// EDC: y = conv(x, h)[D : D+L], D = (K-1)//2, evaluated by overlap-save with the library's own
+// block size (the result of an exact linear convolution does not depend on the block size).
+// =============================================================================================
+namespace {
+
+struct EdcGeom {
+    int nfft;        // block FFT size
+    int d;           // hop = nfft - K + 1 valid outputs per block
+    int64_t nblk;    // blocks per mode
+};
+EdcGeom edc_geom(int64_t L, int K) {
+    EdcGeom g;
+    int nfft = 4096;
+    while (nfft < 8 * K) nfft *= 2;  // keep the overlap redundancy <= 1/8
+    g.nfft = nfft;
+    g.d = nfft - K + 1;
+    g.nblk = (L + g.d - 1) / g.d;
+    return g;
+}
+
+// seg[m][b][t] = x[m][b*d + D - (K-1) + t]  (zero outside [0, L))
+__global__ void k_edc_gather(const float2* __restrict__ x, float2* __restrict__ seg, int64_t L, int nfft,
+                             int d, int64_t nblk, int shift /* D-(K-1) */, int nModes) {
+    const int64_t total = (int64_t)nModes * nblk * nfft;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int t = (int)(i % nfft);
+        int64_t mb = i / nfft;
+        int64_t b = mb % nblk;
+        int64_t m = mb / nblk;
+        int64_t src = b * d + shift + t;
+        float2 v = make_float2(0.f, 0.f);
+        if (src >= 0 && src < L) v = __ldg(x + m * L + src);
+        seg[i] = v;
+    }
+}
+// seg[m][b][k] *= Hf[k] / nfft
+__global__ void k_edc_mul(float2* __restrict__ seg, const float2* __restrict__ Hf, int64_t total, int nfft,
+                          float inv_n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float2 h = __ldg(Hf + (i % nfft));
+        float2 v = cmul(seg[i], h);
+        seg[i] = make_float2(v.x * inv_n, v.y * inv_n);
+    }
+}
+// y[m][b*d + j] = seg[m][b][K-1+j], j in [0, d)
+__global__ void k_edc_scatter(const float2* __restrict__ seg, float2* __restrict__ y, int64_t L, int nfft,
+                              int d, int64_t nblk, int K, int nModes) {
+    const int64_t total = (int64_t)nModes * nblk * d;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int j = (int)(i % d);
+        int64_t mb = i / d;
+        int64_t b = mb % nblk;
+        int64_t m = mb / nblk;
+        int64_t dst = b * d + j;
+        if (dst < L) y[m * L + dst] = seg[mb * nfft + (K - 1) + j];
+    }
+}
+__global__ void k_edc_pad_taps(const float2* __restrict__ h, float2* __restrict__ hp, int K, int nfft) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nfft; i += gridDim.x * blockDim.x)
+        hp[i] = i < K ? h[i] : make_float2(0.f, 0.f);
+}
+
+}  // namespace
+
+extern "C" int64_t ocb_edc_workspace_bytes(int64_t L, int nModes, int K) {
+    if (L <= 0 || nModes <= 0 || K <= 0) return -1;
+    EdcGeom g = edc_geom(L, K);
+    return (int64_t)nModes * g.nblk * g.nfft * 8 + (int64_t)g.nfft * 8 + 512;
+}
+
+extern "C" int ocb_edc_run(const void* x_rows, void* y_rows, int64_t L, int nModes, const void* h_taps, int K,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+    OCB_REQUIRE(x_rows && y_rows && h_taps && workspace, "edc_run: NULL argument");
+    OCB_REQUIRE(L > 0 && nModes > 0 && K > 0, "edc_run: bad sizes");
+    OCB_REQUIRE(workspace_bytes >= ocb_edc_workspace_bytes(L, nModes, K), "edc_run: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    EdcGeom g = edc_geom(L, K);
+    const int D = (K - 1) / 2;  // core.py:1004
+    float2* Hf = (float2*)workspace;
+    float2* seg = (float2*)((char*)workspace + (((int64_t)g.nfft * 8 + 255) / 256) * 256);
+    const int64_t nseg = (int64_t)nModes * g.nblk;
+    OCB_REQUIRE(nseg < (1ll << 31), "edc_run: too many blocks");
+
+    cufftHandle ph, pb;
+    OCB_CUFFT(cufftPlan1d(&ph, g.nfft, CUFFT_C2C, 1));
+    int n[1] = {g.nfft};
+    cufftResult r = cufftPlanMany(&pb, 1, n, nullptr, 1, g.nfft, nullptr, 1, g.nfft, CUFFT_C2C, (int)nseg);
+    if (r != CUFFT_SUCCESS) { cufftDestroy(ph); return fail("edc_run: cufftPlanMany failed", __FILE__, __LINE__); }
+    int rc = 0;
+    do {
+        if (cufftSetStream(ph, st) != CUFFT_SUCCESS || cufftSetStream(pb, st) != CUFFT_SUCCESS) { rc = fail("edc_run: cufftSetStream", __FILE__, __LINE__); break; }
+        k_edc_pad_taps<<<grid_for(g.nfft, 256, 1), 256, 0, st>>>((const float2*)h_taps, Hf, K, g.nfft);
+        launch_counter()++;
+        if (cufftExecC2C(ph, Hf, Hf, CUFFT_FORWARD) != CUFFT_SUCCESS) { rc = fail("edc_run: fft(h)", __FILE__, __LINE__); break; }  // core.py:1020
+        k_edc_gather<<<grid_for(nseg * g.nfft, 256, 4), 256, 0, st>>>((const float2*)x_rows, seg, L, g.nfft, g.d, g.nblk, D - (K - 1), nModes);
+        launch_counter()++;
+        if (cufftExecC2C(pb, seg, seg, CUFFT_FORWARD) != CUFFT_SUCCESS) { rc = fail("edc_run: fft(blocks)", __FILE__, __LINE__); break; }
+        k_edc_mul<<<grid_for(nseg * g.nfft, 256, 4), 256, 0, st>>>(seg, Hf, nseg * g.nfft, g.nfft, 1.0f / (float)g.nfft);
+        launch_counter()++;
+        if (cufftExecC2C(pb, seg, seg, CUFFT_INVERSE) != CUFFT_SUCCESS) { rc = fail("edc_run: ifft(blocks)", __FILE__, __LINE__); break; }
+        k_edc_scatter<<<grid_for(nseg * g.d, 256, 4), 256, 0, st>>>(seg, (float2*)y_rows, L, g.nfft, g.d, g.nblk, K, nModes);
+        launch_counter()++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = fail(cudaGetErrorString(e), __FILE__, __LINE__); break; }
+        e = cudaStreamSynchronize(st);  // plans are destroyed below
+        if (e != cudaSuccess) { rc = fail(cudaGetErrorString(e), __FILE__, __LINE__); break; }
+    } while (0);
+    cufftDestroy(ph);
+    cufftDestroy(pb);
+    return rc;
+}
+
+// =============================================================================================
+// Adaptive MIMO equalizer: one persistent warp per independent stream.  Lane l owns taps
+// t = l + 32 j (j < TPL) of all NM*NM sub-filters in registers; the per-symbol dot products are
+// butterfly-reduced with warp shuffles; the tap update stays in registers.
+// Tap layout: H[(m + n*NM), t] = tap t from input mode n to output mode m (equalization.py:467).
+// =============================================================================================
+namespace {
+
+template <int NM, int TPL, bool WL>
+__global__ void __launch_bounds__(128)
+k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* __restrict__ Hg,
+          float2* __restrict__ HWg, float2* __restrict__ Y, float* __restrict__ ERR, float2* __restrict__ HIT,
+          int nStreams, int64_t xStride, int64_t refStride, int64_t yStride, int64_t errStride,
+          int64_t errModeStride, int64_t L, int nTaps, int SpS, int alg, float mu,
+          const float2* __restrict__ constSymb, int M, const float* __restrict__ radii, int nR, float Rcma) {
+    const int lane = threadIdx.x & 31;
+    const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (stream >= nStreams) return;
+    const float2* x = X + (int64_t)stream * xStride;
+    const float2* ref = REF ? REF + (int64_t)stream * refStride : nullptr;
+    float2* Hs = Hg + (int64_t)stream * NM * NM * nTaps;
+    float2* HWs = WL ? HWg + (int64_t)stream * NM * NM * nTaps : nullptr;
+    float2* y = Y + (int64_t)stream * yStride;
+    float* err = ERR + (int64_t)stream * errStride;
+    float2* hit = HIT ? HIT + (int64_t)stream * L * NM * NM * nTaps : nullptr;
+
+    float2 H[NM * NM][TPL], HW[WL ? NM * NM : 1][TPL];
+#pragma unroll
+    for (int r = 0; r < NM * NM; ++r)
+#pragma unroll
+        for (int j = 0; j < TPL; ++j) {
+            int t = lane + 32 * j;
+            H[r][j] = t < nTaps ? Hs[r * nTaps + t] : make_float2(0.f, 0.f);
+            if (WL) HW[r][j] = t < nTaps ? HWs[r * nTaps + t] : make_float2(0.f, 0.f);
+        }
+
+    auto load_window = [&](int64_t ind, float2 (&w)[NM][TPL]) {
+#pragma unroll
+        for (int j = 0; j < TPL; ++j) {
+            int t = lane + 32 * j;
+            const float2* p = x + (ind * SpS + t) * NM;
+#pragma unroll
+            for (int n = 0; n < NM; ++n) w[n][j] = (t < nTaps) ? __ldg(p + n) : make_float2(0.f, 0.f);
+        }
+    };
+
+    float2 w[NM][TPL], wn[NM][TPL];
+    if (L > 0) load_window(0, w);
+    float prev_err[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) prev_err[m] = 0.f;
+
+    for (int64_t ind = 0; ind < L; ++ind) {
+        if (ind + 1 < L) load_window(ind + 1, wn);  // prefetch: independent of the tap recurrence
+
+        // ---- filter: out[m] = Σ_n H[m + n NM, :] · x_n[window]   (equalization.py:464-471)
+        float2 o[NM];
+        float nrm[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int n = 0; n < NM; ++n)
+#pragma unroll
+                for (int j = 0; j < TPL; ++j) {
+                    float2 p = cmul(H[m + n * NM][j], w[n][j]);
+                    acc.x += p.x; acc.y += p.y;
+                    if (WL) {
+                        float2 q = cmul_conj(HW[m + n * NM][j], w[n][j]);  // H_ · conj(x)
+                        acc.x += q.x; acc.y += q.y;
+                    }
+                }
+            o[m] = acc;
+        }
+        if (alg == OCB_ALG_NLMS) {
+#pragma unroll
+            for (int n = 0; n < NM; ++n) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < TPL; ++j) s += cabs2(w[n][j]);
+                nrm[n] = s;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                o[m].x += __shfl_xor_sync(0xffffffffu, o[m].x, off);
+                o[m].y += __shfl_xor_sync(0xffffffffu, o[m].y, off);
+            }
+            if (alg == OCB_ALG_NLMS) {
+#pragma unroll
+                for (int n = 0; n < NM; ++n) nrm[n] += __shfl_xor_sync(0xffffffffu, nrm[n], off);
+            }
+        }
+        if (lane < NM) {
+            float2 sel = o[0];
+#pragma unroll
+            for (int m = 1; m < NM; ++m) if (lane == m) sel = o[m];
+            y[ind * NM + lane] = sel;  // equalization.py:473
+        }
+
+        // ---- error term g_m and squared error, per algorithm
+        float2 g[NM];
+        float esq[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            const float a2 = cabs2(o[m]);
+            if (alg == OCB_ALG_CMA) {  // :826-829
+                float e = Rcma - a2;
+                g[m] = make_float2(e * o[m].x, e * o[m].y);
+                esq[m] = e * e;
+            } else if (alg == OCB_ALG_RDE || alg == OCB_ALG_DARDE) {  // :887-894, :953-959
+                float Rd;
+                if (alg == OCB_ALG_RDE) {
+                    float r = sqrtf(a2);
+                    float best = fabsf(radii[0] - r);
+                    Rd = radii[0];
+                    for (int i = 1; i < nR; ++i) {
+                        float dd = fabsf(radii[i] - r);
+                        if (dd < best) { best = dd; Rd = radii[i]; }
+                    }
+                } else {
+                    float2 s = __ldg(ref + ind * NM + m);
+                    Rd = sqrtf(cabs2(s));
+                }
+                float e = Rd * Rd - a2;
+                g[m] = make_float2(e * o[m].x, e * o[m].y);
+                esq[m] = e * e;
+            } else if (alg == OCB_ALG_NLMS) {  // :556
+                float2 s = __ldg(ref + ind * NM + m);
+                g[m] = make_float2(s.x - o[m].x, s.y - o[m].y);
+                esq[m] = cabs2(g[m]);
+            } else if (alg == OCB_ALG_DDLMS) {  // :688-691  nearest constellation point, first index on ties
+                float best = 3.4e38f;
+                int bi = 0x7fffffff;
+                for (int c = lane; c < M; c += 32) {
+                    float2 s = __ldg(constSymb + c);
+                    float dd = cabs2(make_float2(o[m].x - s.x, o[m].y - s.y));
+                    if (dd < best) { best = dd; bi = c; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                float2 s = __ldg(constSymb + bi);
+                g[m] = make_float2(s.x - o[m].x, s.y - o[m].y);
+                esq[m] = cabs2(g[m]);
+            } else {  // static: no update (:505-506)
+                g[m] = make_float2(0.f, 0.f);
+                esq[m] = prev_err[m];
+            }
+            prev_err[m] = esq[m];
+        }
+        if (lane < NM) {
+            float sel = esq[0];
+#pragma unroll
+            for (int m = 1; m < NM; ++m) if (lane == m) sel = esq[m];
+            err[(int64_t)lane * errModeStride + ind] = sel;
+        }
+
+        // ---- tap update: H[m + n NM, :] += mu g_m conj(x_n)   (:838-840 and siblings)
+        if (alg != OCB_ALG_STATIC) {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const float2 wg = make_float2(mu * g[m].x, mu * g[m].y);
+#pragma unroll
+                for (int n = 0; n < NM; ++n) {
+                    const float inv = (alg == OCB_ALG_NLMS) ? 1.0f / nrm[n] : 1.0f;
+#pragma unroll
+                    for (int j = 0; j < TPL; ++j) {
+                        float2 xin = w[n][j];
+                        if (alg == OCB_ALG_NLMS) { xin.x *= inv; xin.y *= inv; }  // :563
+                        float2 u = cmul_conj(wg, xin);
+                        H[m + n * NM][j].x += u.x; H[m + n * NM][j].y += u.y;
+                        if (WL) {
+                            float2 v = cmul(wg, xin);
+                            HW[m + n * NM][j].x += v.x; HW[m + n * NM][j].y += v.y;
+                        }
+                    }
+                }
+            }
+        }
+        if (hit) {  // storeCoeff (:511-512): Hiter[:, :, ind] = H, stored as (L, NM², nTaps)
+#pragma unroll
+            for (int r = 0; r < NM * NM; ++r)
+#pragma unroll
+                for (int j = 0; j < TPL; ++j) {
+                    int t = lane + 32 * j;
+                    if (t < nTaps) hit[(ind * NM * NM + r) * nTaps + t] = H[r][j];
+                }
+        }
+#pragma unroll
+        for (int n = 0; n < NM; ++n)
+#pragma unroll
+            for (int j = 0; j < TPL; ++j) w[n][j] = wn[n][j];
+    }
+
+#pragma unroll
+    for (int r = 0; r < NM * NM; ++r)
+#pragma unroll
+        for (int j = 0; j < TPL; ++j) {
+            int t = lane + 32 * j;
+            if (t < nTaps) {
+                Hs[r * nTaps + t] = H[r][j];
+                if (WL) HWs[r * nTaps + t] = HW[r][j];
+            }
+        }
+}
+
+template <int NM, int TPL>
+int launch_mimo(bool wl, int grid, int block, cudaStream_t st, const float2* X, const float2* REF, float2* H,
+                float2* HW, float2* Y, float* ERR, float2* HIT, int nStreams, int64_t xs, int64_t rs, int64_t ys,
+                int64_t es, int64_t ems, int64_t L, int nTaps,
+                int SpS, int alg, float mu, const float2* cs, int M, const float* radii, int nR, float Rcma) {
+    if (wl) OCB_LAUNCH((k_mimo_eq<NM, TPL, true>), grid, block, 0, st, X, REF, H, HW, Y, ERR, HIT, nStreams, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
+    else OCB_LAUNCH((k_mimo_eq<NM, TPL, false>), grid, block, 0, st, X, REF, H, HW, Y, ERR, HIT, nStreams, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hwl, void* y, void* errSq,
+                               void* Hiter, int nStreams, int64_t nSamp, int64_t x_stream_stride,
+                               int64_t ref_stream_stride, int64_t y_stream_stride, int64_t err_stream_stride,
+                               int64_t err_mode_stride, int64_t L, int nModes, int nTaps, int SpS,
+                               int alg, float mu, const void* constSymb, int M, const void* radii, int nR,
+                               float Rcma, int runWL, void* stream) {
+    OCB_REQUIRE(x && H && y && errSq, "mimo_eq_run: NULL argument");
+    OCB_REQUIRE(nStreams > 0 && L >= 0 && nSamp > 0, "mimo_eq_run: bad sizes");
+    OCB_REQUIRE(nModes == 1 || nModes == 2 || nModes == 4, "mimo_eq_run: nModes must be 1, 2 or 4");
+    OCB_REQUIRE(nTaps >= 1 && nTaps <= 128, "mimo_eq_run: nTaps must be in [1, 128]");
+    OCB_REQUIRE(SpS >= 1, "mimo_eq_run: SpS must be >= 1");
+    OCB_REQUIRE(alg >= OCB_ALG_CMA && alg <= OCB_ALG_STATIC,
+                "Equalization algorithm not specified (or incorrectly specified).");  // equalization.py:507-510
+    OCB_REQUIRE(L == 0 || (L - 1) * SpS + nTaps <= nSamp, "mimo_eq_run: window runs past the end of the input");
+    if (alg == OCB_ALG_NLMS || alg == OCB_ALG_DARDE) OCB_REQUIRE(ref != nullptr, "mimo_eq_run: reference symbols required");
+    if (alg == OCB_ALG_RDE) OCB_REQUIRE(radii && nR >= 1, "mimo_eq_run: radii required for RDE");
+    if (alg == OCB_ALG_DDLMS) OCB_REQUIRE(constSymb && M >= 1, "mimo_eq_run: constellation required for DD-LMS");
+    if (runWL) OCB_REQUIRE(Hwl != nullptr, "mimo_eq_run: runWL needs the augmented taps H_");
+    if (L == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpb = nStreams >= 4 * kNumSMs ? 4 : 1;  // warps (streams) per CTA
+    const int grid = (nStreams + wpb - 1) / wpb, block = 32 * wpb;
+    const int tpl = (nTaps + 31) / 32;
+#define OCB_MIMO_CASE(NM_, TPL_)                                                                               \
+    if (nModes == NM_ && tpl == TPL_)                                                                          \
+        return launch_mimo<NM_, TPL_>(runWL != 0, grid, block, st, (const float2*)x, (const float2*)ref,       \
+                                      (float2*)H, (float2*)Hwl, (float2*)y, (float*)errSq, (float2*)Hiter,     \
+                                      nStreams, x_stream_stride, ref_stream_stride, y_stream_stride,           \
+                                      err_stream_stride, err_mode_stride, L, nTaps, SpS, alg, mu,              \
+                                      (const float2*)constSymb, M,                                             \
+                                      (const float*)radii, nR, Rcma);
+    OCB_MIMO_CASE(1, 1) OCB_MIMO_CASE(1, 2) OCB_MIMO_CASE(1, 3) OCB_MIMO_CASE(1, 4)
+    OCB_MIMO_CASE(2, 1) OCB_MIMO_CASE(2, 2) OCB_MIMO_CASE(2, 3) OCB_MIMO_CASE(2, 4)
+    OCB_MIMO_CASE(4, 1) OCB_MIMO_CASE(4, 2)
+#undef OCB_MIMO_CASE
+    return fail("mimo_eq_run: unsupported (nModes, nTaps) combination", __FILE__, __LINE__);
+}
+
+// =============================================================================================
+// Blind phase search (float64, like the reference): per (mode, symbol, test phase) the minimum
+// squared distance to the constellation, then a centred (2N+1)-window sum and an argmin over
+// the B test phases (first index on ties).  One CTA = one tile of symbols of one mode; the
+// dmin tile (B x (TS+2N)) lives in shared memory.
+// =============================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_bps(const double2* __restrict__ X, int64_t L, const double2* __restrict__ cs, int M, int B, int Nh, int TS,
+      int32_t* __restrict__ idx_out, double* __restrict__ ph_out) {
+    extern __shared__ double sm[];
+    const int W = TS + 2 * Nh;            // tile width incl. halo
+    double* dmin = sm;                    // [B][W]
+    double2* rot = (double2*)(dmin + (size_t)B * W);  // [B]
+    double2* csm = rot + B;               // [M]
+    const int mode = blockIdx.y;
+    const int64_t k0 = (int64_t)blockIdx.x * TS;
+    const int nModes = gridDim.y;  // samples are interleaved (L, nModes) like the reference arrays
+
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        double phi = ((double)b * (M_PI / 2.0)) / (double)B;  // carrierRecovery.py:199
+        double s, c;
+        sincos(phi, &s, &c);
+        rot[b] = make_double2(c, s);
+    }
+    for (int c = threadIdx.x; c < M; c += blockDim.x) csm[c] = cs[c];
+    __syncthreads();
+
+    // phase A: dmin[b][j] for symbol k0 - Nh + j  (zero-padded outside [0, L): :203-206)
+    for (int i = threadIdx.x; i < B * W; i += blockDim.x) {
+        const int j = i % W, b = i / W;
+        const int64_t k = k0 - Nh + j;
+        double2 v = make_double2(0.0, 0.0);
+        if (k >= 0 && k < L) v = X[k * nModes + mode];
+        const double2 r = rot[b];
+        const double zr = v.x * r.x - v.y * r.y, zi = v.x * r.y + v.y * r.x;
+        double best = 1.0e300;
+        for (int c = 0; c < M; ++c) {
+            const double dr = zr - csm[c].x, di = zi - csm[c].y;
+            const double dd = dr * dr + di * di;  // :216
+            best = fmin(best, dd);                // :217
+        }
+        dmin[(size_t)b * W + j] = best;
+    }
+    __syncthreads();
+
+    // phase B: window sums + argmin over b  (:218-221)
+    for (int j = threadIdx.x; j < TS; j += blockDim.x) {
+        const int64_t k = k0 + j;
+        if (k >= L) continue;
+        double best = 1.0e300;
+        int bi = 0;
+        for (int b = 0; b < B; ++b) {
+            const double* row = dmin + (size_t)b * W + j;
+            double s = 0.0;
+            for (int t = 0; t <= 2 * Nh; ++t) s += row[t];
+            if (s < best) { best = s; bi = b; }
+        }
+        idx_out[k * nModes + mode] = bi;
+        ph_out[k * nModes + mode] = ((double)bi * (M_PI / 2.0)) / (double)B;
+    }
+}
+
+}  // namespace
+
+extern "C" int ocb_bps_run(const void* x, int64_t L, int nModes, const void* constSymb, int M, int B, int Nhalf,
+                           void* idx_out, void* phase_out, void* stream) {
+    OCB_REQUIRE(x && constSymb && idx_out && phase_out, "bps_run: NULL argument");
+    OCB_REQUIRE(L > 0 && nModes > 0 && M > 0 && B > 0 && Nhalf >= 0, "bps_run: bad sizes");
+    OCB_REQUIRE(nModes <= 65535, "bps_run: too many modes");
+    cudaStream_t st = (cudaStream_t)stream;
+    int TS = 256;
+    auto smem_for = [&](int ts) { return (size_t)B * (ts + 2 * Nhalf) * 8 + (size_t)(B + M) * 16; };
+    while (TS > 16 && smem_for(TS) > 200 * 1024) TS /= 2;
+    const size_t smem = smem_for(TS);
+    OCB_REQUIRE(smem <= 227 * 1024, "bps_run: B*(window) does not fit in shared memory");
+    OCB_CUDA(cudaFuncSetAttribute(k_bps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((L + TS - 1) / TS), (unsigned)nModes);
+    OCB_LAUNCH(k_bps, grid, 256, smem, st, (const double2*)x, L, (const double2*)constSymb, M, B, Nhalf, TS,
+               (int32_t*)idx_out, (double*)phase_out);
+    return 0;
+}

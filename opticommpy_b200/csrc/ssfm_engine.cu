@@ -1,0 +1,469 @@
+// Host-side driver of the split-step propagators (plan lifecycle + step loops) behind the
+// C-ABI in include/opticomm_b200.h.  cuFFT provides the length-N transforms; every other
+// operation of a step is one of the fused kernels in ssfm_kernels.cuh.
+//
+// Reference control flow restated here (not code): optic/models/channels.py:380-456
+// (manakovSSF), optic/dsp/equalization.py:1088-1161 (manakovDBP), channels.py:215-238 (ssfm).
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/opticomm_b200.h"
+#include "ssfm_kernels.cuh"
+
+using namespace ocb;
+
+namespace ocb {
+std::string& last_error() {
+    static thread_local std::string e;
+    return e;
+}
+int fail(const char* what, const char* file, int line) {
+    char b[768];
+    snprintf(b, sizeof b, "%s (%s:%d)", what, file, line);
+    last_error() = b;
+    return 1;
+}
+int64_t& launch_counter() {
+    static thread_local int64_t c = 0;
+    return c;
+}
+}  // namespace ocb
+
+struct ocb_ssfm_plan {
+    int64_t N = 0;
+    int rows = 0;
+    cufftHandle fft = 0;
+    bool fft_ok = false;
+    size_t fft_work = 0;
+    // workspace partition (device)
+    void* ws = nullptr;
+    int64_t ws_bytes = 0;
+    float2 *Ehd = nullptr, *A = nullptr, *B = nullptr, *G = nullptr, *T1 = nullptr, *T2 = nullptr;
+    float* Pch = nullptr;
+    double* partials = nullptr;  // [max_blocks][3]
+    double* sums = nullptr;      // 3 doubles
+    unsigned* ticket = nullptr;
+    void* fft_area = nullptr;
+    // pinned host mailbox for the convergence scalars
+    double* h_sums = nullptr;
+    // staging for the _host variants
+    void* stage_dev = nullptr;
+    int64_t stage_bytes = 0;
+    int max_blocks = kNumSMs * 8;
+    // table cache keys
+    double t1_h = NAN, t1_a = NAN, t1_b = NAN, t1_scale = NAN;
+};
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int ocb_abi_version(void) { return OCB_ABI_VERSION; }
+extern "C" const char* ocb_last_error(void) { return last_error().c_str(); }
+extern "C" int64_t ocb_launch_count(void) { return launch_counter(); }
+extern "C" void ocb_launch_count_reset(void) { launch_counter() = 0; }
+
+extern "C" int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out) {
+    OCB_REQUIRE(out != nullptr, "plan_create: out is NULL");
+    OCB_REQUIRE(N >= 2 && N < (1ll << 31), "plan_create: N out of range");
+    OCB_REQUIRE(rows >= 1 && rows <= 4096, "plan_create: rows out of range");
+    ocb_ssfm_plan* p = new ocb_ssfm_plan();
+    p->N = N;
+    p->rows = rows;
+    if (cufftCreate(&p->fft) != CUFFT_SUCCESS) { delete p; return fail("cufftCreate failed", __FILE__, __LINE__); }
+    p->fft_ok = true;
+    if (cufftSetAutoAllocation(p->fft, 0) != CUFFT_SUCCESS) { ocb_ssfm_plan_destroy(p); return fail("cufftSetAutoAllocation failed", __FILE__, __LINE__); }
+    int n[1] = {(int)N};
+    cufftResult r = cufftMakePlanMany(p->fft, 1, n, nullptr, 1, (int)N, nullptr, 1, (int)N, CUFFT_C2C,
+                                      rows, &p->fft_work);
+    if (r != CUFFT_SUCCESS) {
+        ocb_ssfm_plan_destroy(p);
+        char b[128]; snprintf(b, sizeof b, "cufftMakePlanMany failed (%d)", (int)r);
+        return fail(b, __FILE__, __LINE__);
+    }
+    cudaError_t e = cudaHostAlloc((void**)&p->h_sums, 8 * sizeof(double), cudaHostAllocDefault);
+    if (e != cudaSuccess) { ocb_ssfm_plan_destroy(p); return fail("cudaHostAlloc failed", __FILE__, __LINE__); }
+    *out = p;
+    return 0;
+}
+
+extern "C" int64_t ocb_ssfm_plan_workspace_bytes(const ocb_ssfm_plan* p) {
+    if (!p) return -1;
+    const int64_t field = align_up((int64_t)p->rows * p->N * sizeof(float2), 256);
+    int64_t b = 0;
+    b += 4 * field;                                                   // Ehd, A, B, G
+    b += 2 * align_up(p->N * (int64_t)sizeof(float2), 256);           // T1, T2
+    b += align_up(((int64_t)(p->rows + 1) / 2) * p->N * sizeof(float), 256);  // Pch
+    b += align_up((int64_t)p->max_blocks * 3 * sizeof(double), 256);  // partials
+    b += 256;                                                         // sums + ticket
+    b += align_up((int64_t)p->fft_work, 256);
+    return b;
+}
+
+extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int64_t bytes) {
+    OCB_REQUIRE(p && dev_ptr, "bind_workspace: NULL argument");
+    OCB_REQUIRE(bytes >= ocb_ssfm_plan_workspace_bytes(p), "bind_workspace: workspace too small");
+    OCB_REQUIRE(((uintptr_t)dev_ptr & 255) == 0, "bind_workspace: pointer must be 256-byte aligned");
+    const int64_t field = align_up((int64_t)p->rows * p->N * sizeof(float2), 256);
+    char* c = (char*)dev_ptr;
+    p->ws = dev_ptr; p->ws_bytes = bytes;
+    p->Ehd = (float2*)c; c += field;
+    p->A = (float2*)c; c += field;
+    p->B = (float2*)c; c += field;
+    p->G = (float2*)c; c += field;
+    p->T1 = (float2*)c; c += align_up(p->N * (int64_t)sizeof(float2), 256);
+    p->T2 = (float2*)c; c += align_up(p->N * (int64_t)sizeof(float2), 256);
+    p->Pch = (float*)c; c += align_up(((int64_t)(p->rows + 1) / 2) * p->N * sizeof(float), 256);
+    p->partials = (double*)c; c += align_up((int64_t)p->max_blocks * 3 * sizeof(double), 256);
+    p->sums = (double*)c; p->ticket = (unsigned*)(c + 64); c += 256;
+    p->fft_area = c;
+    if (p->fft_work > 0) OCB_CUFFT(cufftSetWorkArea(p->fft, p->fft_area));
+    OCB_CUDA(cudaMemset(p->sums, 0, 256));
+    p->t1_h = NAN;
+    return 0;
+}
+
+extern "C" int ocb_ssfm_plan_destroy(ocb_ssfm_plan* p) {
+    if (!p) return 0;
+    if (p->fft_ok) cufftDestroy(p->fft);
+    if (p->h_sums) cudaFreeHost(p->h_sums);
+    if (p->stage_dev) cudaFree(p->stage_dev);
+    delete p;
+    return 0;
+}
+
+// ---- layout conversion -------------------------------------------------------------------
+extern "C" int ocb_pack_fields(const void* src, int src_dtype, int64_t N, int C, int pairs, void* rows,
+                               void* stream) {
+    OCB_REQUIRE(src && rows && N > 0 && C > 0, "pack_fields: bad argument");
+    OCB_REQUIRE(!pairs || (C % 2 == 0), "pack_fields: pairs layout needs an even column count");
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(N * C, 256, 1);
+    if (src_dtype == OCB_C64) OCB_LAUNCH(k_pack<float2>, g, 256, 0, st, (const float2*)src, (float2*)rows, N, C, pairs);
+    else if (src_dtype == OCB_C128) OCB_LAUNCH(k_pack<double2>, g, 256, 0, st, (const double2*)src, (float2*)rows, N, C, pairs);
+    else return fail("pack_fields: unknown dtype", __FILE__, __LINE__);
+    return 0;
+}
+extern "C" int ocb_unpack_fields(const void* rows, int64_t N, int C, int pairs, void* dst, int dst_dtype,
+                                 void* stream) {
+    OCB_REQUIRE(dst && rows && N > 0 && C > 0, "unpack_fields: bad argument");
+    OCB_REQUIRE(!pairs || (C % 2 == 0), "unpack_fields: pairs layout needs an even column count");
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(N * C, 256, 1);
+    if (dst_dtype == OCB_C64) OCB_LAUNCH(k_unpack<float2>, g, 256, 0, st, (const float2*)rows, (float2*)dst, N, C, pairs);
+    else if (dst_dtype == OCB_C128) OCB_LAUNCH(k_unpack<double2>, g, 256, 0, st, (const float2*)rows, (double2*)dst, N, C, pairs);
+    else return fail("unpack_fields: unknown dtype", __FILE__, __LINE__);
+    return 0;
+}
+
+// ---- small launch helpers --------------------------------------------------------------------
+static int launch_table(ocb_ssfm_plan* p, float2* T, double a, double b, double Fs, double h,
+                        double scale, cudaStream_t st) {
+    OCB_LAUNCH(k_linop_table, grid_for(p->N, 256, 1), 256, 0, st, T, p->N, a, b, Fs, h, scale);
+    return 0;
+}
+static int launch_mul(ocb_ssfm_plan* p, float2* F, const float2* T, cudaStream_t st) {
+    if (p->N % 2 == 0) OCB_LAUNCH(k_mul_table<2>, grid_for(p->N / 2 * p->rows, 256, 1), 256, 0, st, F, T, p->N, p->rows);
+    else OCB_LAUNCH(k_mul_table<1>, grid_for(p->N * p->rows, 256, 1), 256, 0, st, F, T, p->N, p->rows);
+    return 0;
+}
+static int launch_amp(float2* E, int R, int64_t N, double g, double sigma, const float2* noise,
+                      int noise_rows, uint64_t seed, uint64_t stream_id, cudaStream_t st) {
+    OCB_LAUNCH(k_amp, grid_for((int64_t)R * N, 256, 2), 256, 0, st, E, R, N, (float)g, (float)sigma, noise,
+               noise_rows, seed, stream_id);
+    return 0;
+}
+static int nl_grid(const ocb_ssfm_plan* p, int64_t items) {
+    int g = grid_for(items, 256, 1, 8);
+    return g > p->max_blocks ? p->max_blocks : g;
+}
+static int launch_nl(ocb_ssfm_plan* p, bool first, const float2* Ehd, const float2* Efd, const float2* Ec,
+                     float* Pch, float2* out, int64_t N, int K, float cphi, double* partials, double* sums,
+                     unsigned* ticket, cudaStream_t st) {
+    const bool v2 = (N % 2 == 0);
+    const int g = nl_grid(p, v2 ? N / 2 * K : N * K);
+    if (first) {
+        if (v2) OCB_LAUNCH((k_manakov_nl<true, 2>), g, 256, 0, st, Ehd, Efd, Ec, Pch, out, N, K, cphi, partials, sums, ticket);
+        else OCB_LAUNCH((k_manakov_nl<true, 1>), g, 256, 0, st, Ehd, Efd, Ec, Pch, out, N, K, cphi, partials, sums, ticket);
+    } else {
+        if (v2) OCB_LAUNCH((k_manakov_nl<false, 2>), g, 256, 0, st, Ehd, Efd, Ec, Pch, out, N, K, cphi, partials, sums, ticket);
+        else OCB_LAUNCH((k_manakov_nl<false, 1>), g, 256, 0, st, Ehd, Efd, Ec, Pch, out, N, K, cphi, partials, sums, ticket);
+    }
+    return 0;
+}
+static int launch_power_stats(ocb_ssfm_plan* p, const float2* E, int64_t N, int K, cudaStream_t st) {
+    const bool v2 = (N % 2 == 0);
+    const int g = nl_grid(p, v2 ? N / 2 * K : N * K);
+    if (v2) OCB_LAUNCH(k_power_stats<2>, g, 256, 0, st, E, N, K, p->partials, p->sums, p->ticket);
+    else OCB_LAUNCH(k_power_stats<1>, g, 256, 0, st, E, N, K, p->partials, p->sums, p->ticket);
+    return 0;
+}
+static int fetch_sums(ocb_ssfm_plan* p, cudaStream_t st) {
+    OCB_CUDA(cudaMemcpyAsync(p->h_sums, p->sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OCB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int ocb_manakov_nl_pass(const void* Ehd, const void* Efd, const void* Ec, void* Pch, void* out,
+                                   void* sums3_dev, int64_t N, int K, double gamma, double hz, int direction,
+                                   void* stream) {
+    OCB_REQUIRE(Ehd && Ec && Pch && out && N > 0 && K > 0, "nl_pass: bad argument");
+    OCB_REQUIRE(direction == 1 || direction == -1, "nl_pass: direction must be +1 or -1");
+    cudaStream_t st = (cudaStream_t)stream;
+    ocb_ssfm_plan tmp;  // only max_blocks is used
+    const bool first = (Efd == nullptr);
+    double* scratch = nullptr;
+    if (!first) {
+        OCB_REQUIRE(sums3_dev != nullptr, "nl_pass: sums3_dev is NULL");
+        OCB_CUDA(cudaMallocAsync((void**)&scratch, (size_t)tmp.max_blocks * 3 * sizeof(double) + 64, st));
+        OCB_CUDA(cudaMemsetAsync((char*)scratch + (size_t)tmp.max_blocks * 3 * sizeof(double), 0, 64, st));
+    }
+    const double c = (double)direction * hz * (8.0 / 9.0) * gamma * (first ? 1.0 : 0.5);
+    int rc = launch_nl(&tmp, first, (const float2*)Ehd, (const float2*)Efd, (const float2*)Ec, (float*)Pch,
+                       (float2*)out, N, K, (float)c, scratch, (double*)sums3_dev,
+                       scratch ? (unsigned*)((char*)scratch + (size_t)tmp.max_blocks * 3 * sizeof(double)) : nullptr, st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+extern "C" int ocb_edfa_apply(void* rows_inout, int rows, int64_t N, double gain_lin, double noise_var,
+                              int noise_mode, const void* noise_dev, int noise_rows, uint64_t seed,
+                              uint64_t stream_id, void* stream) {
+    OCB_REQUIRE(rows_inout && rows > 0 && N > 0, "edfa_apply: bad argument");
+    OCB_REQUIRE(gain_lin > 0.0 && noise_var >= 0.0, "edfa_apply: gain must be > 0 and noise_var >= 0");
+    if (noise_mode == OCB_NOISE_INJECTED) OCB_REQUIRE(noise_dev && noise_rows > 0, "edfa_apply: injected noise buffer missing");
+    return launch_amp((float2*)rows_inout, rows, N, sqrt(gain_lin),
+                      noise_mode == OCB_NOISE_PHILOX ? sqrt(noise_var / 2.0) : 0.0,
+                      noise_mode == OCB_NOISE_INJECTED ? (const float2*)noise_dev : nullptr,
+                      noise_rows > 0 ? noise_rows : 1, seed, stream_id, (cudaStream_t)stream);
+}
+
+// ---- Manakov SSF / DBP -------------------------------------------------------------------------
+extern "C" int ocb_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manakov_params* q,
+                               const void* noise_dev, const int32_t* save_spans, void* save_dev,
+                               ocb_manakov_stats* stats, void* stream) {
+    OCB_REQUIRE(p && rows_inout && q, "manakov_run: NULL argument");
+    OCB_REQUIRE(p->ws != nullptr, "manakov_run: workspace not bound");
+    OCB_REQUIRE(p->rows % 2 == 0, "manakov_run: plan rows must be even (x/y pairs)");
+    OCB_REQUIRE(q->direction == 1 || q->direction == -1, "manakov_run: direction must be +1/-1");
+    OCB_REQUIRE(q->maxIter >= 1, "manakov_run: maxIter must be >= 1");
+    OCB_REQUIRE(q->Lspan > 0, "manakov_run: Lspan must be > 0");
+    OCB_REQUIRE(q->nlprMethod || q->hz > 0, "manakov_run: hz must be > 0");
+    if (q->nlprMethod) OCB_REQUIRE(q->gamma != 0.0, "manakov_run: nlprMethod=True with gamma=0 divides by zero (channels.py:394)");
+    if (q->amp_mode == OCB_AMP_EDFA && q->direction == 1 && q->noise_mode == OCB_NOISE_INJECTED)
+        OCB_REQUIRE(noise_dev != nullptr, "manakov_run: injected noise buffer missing");
+    OCB_REQUIRE(q->n_save == 0 || (save_spans && save_dev), "manakov_run: snapshot buffers missing");
+
+    cudaStream_t st = (cudaStream_t)stream;
+    OCB_CUFFT(cufftSetStream(p->fft, st));
+    const int64_t N = p->N;
+    const int R = p->rows, K = R / 2;
+    const double dir = (double)q->direction;
+    // argLimOp = -(α/2) + j(β2/2)ω²  (channels.py:368) ; DBP: +(α/2) - j(β2/2)ω² (equalization.py:1077)
+    const double a = -dir * q->alpha_lin / 2.0, b = dir * q->beta2 / 2.0;
+    const size_t field_bytes = (size_t)R * N * sizeof(float2);
+
+    float2* bufs[3] = {(float2*)rows_inout, p->A, p->B};
+    int cur = 0;
+    ocb_manakov_stats S = {0, 0, 0, 0.0, 0.0};
+    double table_h = NAN;
+    int next_save = 0;
+    uint64_t amp_calls = 0;
+
+    for (int span = 1; span <= q->n_spans; ++span) {
+        if (q->direction < 0 && q->amp_mode != OCB_AMP_NONE) {
+            // undo the span gain first (equalization.py:1090-1092)
+            if (launch_amp(bufs[cur], R, N, exp(-q->alpha_lin / 2.0 * q->Lspan), 0.0, nullptr, 1, 0, 0, st)) return 1;
+        }
+        double maxP = 0.0;
+        if (q->nlprMethod) {
+            if (launch_power_stats(p, bufs[cur], N, K, st)) return 1;
+            if (fetch_sums(p, st)) return 1;
+            maxP = p->h_sums[2];
+        }
+        double z = 0.0;
+        while (z < q->Lspan) {  // channels.py:387
+            double hz_;
+            if (q->nlprMethod) {  // channels.py:392-397
+                const double phimax = (8.0 / 9.0) * q->gamma * maxP;
+                const double cand = q->maxNlinPhaseRot / phimax;
+                hz_ = (q->Lspan - z >= cand) ? cand : (q->Lspan - z);
+            } else if (q->Lspan - z < q->hz) {  // channels.py:398-401
+                hz_ = q->Lspan - z;
+            } else {
+                hz_ = q->hz;
+            }
+            if (!(table_h == hz_)) {  // linOperator = exp(argLimOp*hz_/2), rebuilt only when hz_ changes
+                if (launch_table(p, p->T1, a, b, q->Fs, hz_ / 2.0, 1.0 / (double)N, st)) return 1;
+                table_h = hz_;
+            }
+            // first half step: Ehd = ifft(fft(E)·L)    (channels.py:409-410)
+            OCB_CUFFT(cufftExecC2C(p->fft, bufs[cur], p->G, CUFFT_FORWARD));
+            if (launch_mul(p, p->G, p->T1, st)) return 1;
+            OCB_CUFFT(cufftExecC2C(p->fft, p->G, p->Ehd, CUFFT_INVERSE));
+
+            int ec = cur, dst = (cur + 1) % 3;
+            const float c_first = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma);
+            const float c_iter = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma * 0.5);
+            if (launch_nl(p, true, p->Ehd, nullptr, bufs[ec], p->Pch, p->G, N, K, c_first, nullptr, nullptr, nullptr, st)) return 1;
+            for (int it = 0; it < q->maxIter; ++it) {  // channels.py:413
+                // second half step on the rotated field  (channels.py:420-421)
+                OCB_CUFFT(cufftExecC2C(p->fft, p->G, p->G, CUFFT_FORWARD));
+                if (launch_mul(p, p->G, p->T1, st)) return 1;
+                OCB_CUFFT(cufftExecC2C(p->fft, p->G, bufs[dst], CUFFT_INVERSE));
+                // convergence sums + speculative next rotation in one pass (channels.py:424, 436, 414-417)
+                if (launch_nl(p, false, p->Ehd, bufs[dst], bufs[ec], p->Pch, p->G, N, K, c_iter, p->partials, p->sums, p->ticket, st)) return 1;
+                if (fetch_sums(p, st)) return 1;
+                const double lim = sqrt(p->h_sums[0]) / sqrt(p->h_sums[1]);  // channels.py:517-519
+                S.iterations++;
+                S.last_lim = lim;
+                const int third = 3 - ec - dst;
+                ec = dst;      // Ex_conv = Ech_x_fd  (channels.py:426-427)
+                dst = third;
+                if (lim < q->tol) break;  // channels.py:429
+                if (it == q->maxIter - 1) S.nonconverged++;  // channels.py:431-434 (warning only)
+            }
+            cur = ec;  // Ech = Ech_fd (channels.py:438-439)
+            maxP = p->h_sums[2];
+            z += hz_;  // channels.py:441
+            S.steps++;
+            S.z_last_step = hz_;
+        }
+        if (q->direction > 0) {  // amplification (channels.py:443-451)
+            if (q->amp_mode == OCB_AMP_EDFA) {
+                const bool inj = (q->noise_mode == OCB_NOISE_INJECTED);
+                if (launch_amp(bufs[cur], R, N, sqrt(q->edfa_gain_lin), inj ? 0.0 : sqrt(q->edfa_noise_var / 2.0),
+                               inj ? (const float2*)noise_dev : nullptr, K, q->seed, amp_calls++, st)) return 1;
+            } else if (q->amp_mode == OCB_AMP_IDEAL) {
+                if (launch_amp(bufs[cur], R, N, exp(q->alpha_lin / 2.0 * q->Lspan), 0.0, nullptr, 1, 0, 0, st)) return 1;
+            }
+        }
+        if (next_save < q->n_save && save_spans[next_save] == span) {  // channels.py:453-456
+            OCB_CUDA(cudaMemcpyAsync((char*)save_dev + (size_t)next_save * field_bytes, bufs[cur], field_bytes,
+                                     cudaMemcpyDeviceToDevice, st));
+            next_save++;
+        }
+    }
+    if (cur != 0) OCB_CUDA(cudaMemcpyAsync(rows_inout, bufs[cur], field_bytes, cudaMemcpyDeviceToDevice, st));
+    if (stats) *stats = S;
+    return 0;
+}
+
+static int ensure_stage(ocb_ssfm_plan* p, int64_t bytes) {
+    if (p->stage_bytes >= bytes) return 0;
+    if (p->stage_dev) cudaFree(p->stage_dev);
+    p->stage_dev = nullptr; p->stage_bytes = 0;
+    OCB_CUDA(cudaMalloc(&p->stage_dev, (size_t)bytes));
+    p->stage_bytes = bytes;
+    return 0;
+}
+
+extern "C" int ocb_manakov_run_host(ocb_ssfm_plan* p, const void* Ei_host, int in_dtype, void* Eo_host,
+                                    int out_dtype, const ocb_manakov_params* q, const void* noise_host,
+                                    const int32_t* save_spans, ocb_manakov_stats* stats, void* stream) {
+    OCB_REQUIRE(p && Ei_host && Eo_host && q, "manakov_run_host: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t N = p->N;
+    const int R = p->rows, K = R / 2;
+    const int64_t in_elem = in_dtype == OCB_C128 ? 16 : 8, out_elem = out_dtype == OCB_C128 ? 16 : 8;
+    const int nsnap = q->n_save > 0 ? q->n_save : 1;
+    const int64_t field = align_up((int64_t)R * N * 8, 256);
+    // staging: [raw in/out (max of both)] [rows] [snapshots] [noise]
+    const int64_t raw = align_up(std::max<int64_t>(R * N * in_elem, (int64_t)R * nsnap * N * out_elem), 256);
+    const int64_t noise_b = noise_host ? align_up((int64_t)K * N * 8, 256) : 0;
+    if (ensure_stage(p, raw + field + (q->n_save > 0 ? (int64_t)nsnap * field : 0) + noise_b)) return 1;
+    char* c = (char*)p->stage_dev;
+    void* d_raw = c; c += raw;
+    void* d_rows = c; c += field;
+    void* d_save = nullptr;
+    if (q->n_save > 0) { d_save = c; c += (int64_t)nsnap * field; }
+    void* d_noise = nullptr;
+    if (noise_host) { d_noise = c; }
+
+    OCB_CUDA(cudaMemcpyAsync(d_raw, Ei_host, (size_t)(R * N * in_elem), cudaMemcpyHostToDevice, st));
+    if (noise_host) OCB_CUDA(cudaMemcpyAsync(d_noise, noise_host, (size_t)K * N * 8, cudaMemcpyHostToDevice, st));
+    if (ocb_pack_fields(d_raw, in_dtype, N, R, 1, d_rows, stream)) return 1;
+    if (ocb_manakov_run(p, d_rows, q, d_noise, save_spans, d_save, stats, stream)) return 1;
+    if (q->n_save > 0) {
+        // output (N, 2K*n_save): snapshot s occupies columns [2K s, 2K (s+1))  (channels.py:454-455, K=1)
+        // unpack each snapshot into a (N, R) block, then the host interleaves blocks column-wise.
+        for (int s = 0; s < nsnap; ++s)
+            if (ocb_unpack_fields((char*)d_save + (int64_t)s * field, N, R, 1,
+                                  (char*)d_raw + (int64_t)s * R * N * out_elem, out_dtype, stream)) return 1;
+        OCB_CUDA(cudaMemcpyAsync(Eo_host, d_raw, (size_t)((int64_t)nsnap * R * N * out_elem), cudaMemcpyDeviceToHost, st));
+    } else {
+        if (ocb_unpack_fields(d_rows, N, R, 1, d_raw, out_dtype, stream)) return 1;
+        OCB_CUDA(cudaMemcpyAsync(Eo_host, d_raw, (size_t)(R * N * out_elem), cudaMemcpyDeviceToHost, st));
+    }
+    OCB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- scalar NLSE ---------------------------------------------------------------------------------
+extern "C" int ocb_nlse_run(ocb_ssfm_plan* p, void* row_inout, const ocb_nlse_params* q, const void* noise_dev,
+                            void* stream) {
+    OCB_REQUIRE(p && row_inout && q, "nlse_run: NULL argument");
+    OCB_REQUIRE(p->ws != nullptr, "nlse_run: workspace not bound");
+    OCB_REQUIRE(q->n_steps >= 0 && q->n_spans >= 0, "nlse_run: negative step/span count");
+    if (q->amp_mode == OCB_AMP_EDFA && q->noise_mode == OCB_NOISE_INJECTED)
+        OCB_REQUIRE(noise_dev != nullptr, "nlse_run: injected noise buffer missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    OCB_CUFFT(cufftSetStream(p->fft, st));
+    const int64_t N = p->N;
+    const int R = p->rows;
+    float2* E = (float2*)row_inout;
+    const double a = -q->alpha_lin / 2.0, b = q->beta2 / 2.0;
+    // T1 = L/N (entering / leaving the frequency domain), T2 = L²/N (between two steps):
+    // channels.py:221 and :229 are two multiplies by the same operator, merged here.
+    if (launch_table(p, p->T1, a, b, q->Fs, q->hz / 2.0, 1.0 / (double)N, st)) return 1;
+    if (launch_table(p, p->T2, a, b, q->Fs, q->hz, 1.0 / (double)N, st)) return 1;
+    p->t1_h = NAN;
+    const float cnl = (float)(q->gamma * q->hz);
+    const int64_t total = (int64_t)R * N;
+    for (int span = 0; span < q->n_spans; ++span) {
+        if (q->n_steps > 0) {
+            OCB_CUFFT(cufftExecC2C(p->fft, E, E, CUFFT_FORWARD));  // channels.py:216
+            for (int s = 0; s < q->n_steps; ++s) {
+                if (launch_mul(p, E, s == 0 ? p->T1 : p->T2, st)) return 1;  // :221 (+ :229 of the previous step)
+                OCB_CUFFT(cufftExecC2C(p->fft, E, E, CUFFT_INVERSE));        // :224
+                if (total % 2 == 0 && N % 2 == 0) OCB_LAUNCH(k_nlse_phase<2>, grid_for(total / 2, 256, 1), 256, 0, st, E, total, cnl);  // :225
+                else OCB_LAUNCH(k_nlse_phase<1>, grid_for(total, 256, 1), 256, 0, st, E, total, cnl);
+                OCB_CUFFT(cufftExecC2C(p->fft, E, E, CUFFT_FORWARD));        // :228
+            }
+            if (launch_mul(p, E, p->T1, st)) return 1;                       // :229 of the last step
+            OCB_CUFFT(cufftExecC2C(p->fft, E, E, CUFFT_INVERSE));            // :232
+        }
+        if (q->amp_mode == OCB_AMP_EDFA) {  // :233-234
+            const bool inj = (q->noise_mode == OCB_NOISE_INJECTED);
+            if (launch_amp(E, R, N, sqrt(q->edfa_gain_lin), inj ? 0.0 : sqrt(q->edfa_noise_var / 2.0),
+                           inj ? (const float2*)noise_dev : nullptr, R, q->seed, (uint64_t)span, st)) return 1;
+        } else if (q->amp_mode == OCB_AMP_IDEAL) {  // :235-236
+            if (launch_amp(E, R, N, exp(q->alpha_lin / 2.0 * q->n_steps * q->hz), 0.0, nullptr, 1, 0, 0, st)) return 1;
+        }
+    }
+    return 0;
+}
+
+extern "C" int ocb_nlse_run_host(ocb_ssfm_plan* p, const void* Ei_host, int in_dtype, void* Eo_host, int out_dtype,
+                                 const ocb_nlse_params* q, const void* noise_host, void* stream) {
+    OCB_REQUIRE(p && Ei_host && Eo_host && q, "nlse_run_host: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t N = p->N;
+    const int R = p->rows;
+    const int64_t in_elem = in_dtype == OCB_C128 ? 16 : 8, out_elem = out_dtype == OCB_C128 ? 16 : 8;
+    const int64_t raw = align_up(R * N * std::max(in_elem, out_elem), 256);
+    const int64_t field = align_up((int64_t)R * N * 8, 256);
+    if (ensure_stage(p, raw + field + (noise_host ? field : 0))) return 1;
+    char* c = (char*)p->stage_dev;
+    void* d_raw = c; c += raw;
+    void* d_rows = c; c += field;
+    void* d_noise = noise_host ? c : nullptr;
+    OCB_CUDA(cudaMemcpyAsync(d_raw, Ei_host, (size_t)(R * N * in_elem), cudaMemcpyHostToDevice, st));
+    if (noise_host) OCB_CUDA(cudaMemcpyAsync(d_noise, noise_host, (size_t)R * N * 8, cudaMemcpyHostToDevice, st));
+    if (ocb_pack_fields(d_raw, in_dtype, N, R, 0, d_rows, stream)) return 1;
+    if (ocb_nlse_run(p, d_rows, q, d_noise, stream)) return 1;
+    if (ocb_unpack_fields(d_rows, N, R, 0, d_raw, out_dtype, stream)) return 1;
+    OCB_CUDA(cudaMemcpyAsync(Eo_host, d_raw, (size_t)(R * N * out_elem), cudaMemcpyDeviceToHost, st));
+    OCB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -1,0 +1,311 @@
+// Elementwise / reduction kernels of the split-step propagators (cuFFT-driven engine).
+// All fields are planar rows[R][N] complex64 (R = 2K: x rows then y rows).
+#pragma once
+#include "common.cuh"
+
+namespace ocb {
+
+// ------------------------------------------------------------------------------------------
+// Linear-operator table:  T[k] = scale * exp( (a + j b ω_k²) · h )^{pw}
+//   ω_k = 2π Fs fftfreq(N)[k]                      (channels.py:203, 360)
+//   a = ∓α/2, b = ±β2/2                            (channels.py:368 ; equalization.py:1077)
+//   h = hz/2                                       (channels.py:213, 406)
+// The phase is evaluated in float64 (it reaches 1e2..1e3 rad at the band edge) and only the
+// final (cos, sin) pair is rounded to float32.
+// ------------------------------------------------------------------------------------------
+__global__ void k_linop_table(float2* __restrict__ T, int64_t N, double a, double b, double Fs,
+                              double h, double scale) {
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < N;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        int64_t kk = (k <= (N - 1) / 2) ? k : k - N;  // numpy.fft.fftfreq bin order
+        double w = two_pi * Fs * ((double)kk / (double)N);
+        double ph = b * (w * w) * h;
+        double amp = scale * exp(a * h);
+        double s, c;
+        sincos(ph, &s, &c);
+        T[k] = make_float2((float)(amp * c), (float)(amp * s));
+    }
+}
+
+// F[r][k] *= T[k]   (frequency-domain multiply; 1/N of the unnormalised inverse cuFFT is folded in T)
+template <int VEC>
+__global__ void k_mul_table(float2* __restrict__ F, const float2* __restrict__ T, int64_t N, int R) {
+    const int64_t per_row = N / VEC;
+    const int64_t total = per_row * R;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = (i % per_row) * VEC;
+        int64_t off = (i / per_row) * N + k;
+        if (VEC == 2) {
+            float4 f = *reinterpret_cast<const float4*>(F + off);
+            float4 t = ldg4(T + k);
+            float2 a = cmul(make_float2(f.x, f.y), make_float2(t.x, t.y));
+            float2 b = cmul(make_float2(f.z, f.w), make_float2(t.z, t.w));
+            stg4(F + off, make_float4(a.x, a.y, b.x, b.y));
+        } else {
+            F[off] = cmul(F[off], __ldg(T + k));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Block-level reduction of (sum, sum, max) with a deterministic "last block finalises" tail.
+// partials: [gridDim.x][3] doubles ; out: 3 doubles ; ticket: 1 uint (self-resetting).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_reduce3_finalize(float s0, float s1, float m,
+                                                       double* __restrict__ partials,
+                                                       double* __restrict__ out,
+                                                       unsigned* __restrict__ ticket) {
+    __shared__ double sh0[32], sh1[32], sh2[32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    // warp level in float (<= 32 addends), block level in double
+    float w0 = warp_sum(s0), w1 = warp_sum(s1), wm = warp_max(m);
+    if (lane == 0) { sh0[wid] = (double)w0; sh1[wid] = (double)w1; sh2[wid] = (double)wm; }
+    __syncthreads();
+    if (wid == 0) {
+        double a = lane < nw ? sh0[lane] : 0.0, b = lane < nw ? sh1[lane] : 0.0;
+        double c = lane < nw ? sh2[lane] : 0.0;
+        a = warp_sum(a); b = warp_sum(b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+        if (lane == 0) {
+            partials[3 * blockIdx.x + 0] = a;
+            partials[3 * blockIdx.x + 1] = b;
+            partials[3 * blockIdx.x + 2] = c;
+            __threadfence();
+            unsigned t = atomicAdd(ticket, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // fixed-order strided accumulation -> deterministic for a fixed grid
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        a += __ldcg(partials + 3 * i + 0);
+        b += __ldcg(partials + 3 * i + 1);
+        c = fmax(c, __ldcg(partials + 3 * i + 2));
+    }
+    a = warp_sum(a); b = warp_sum(b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+    __syncthreads();
+    if (lane == 0) { sh0[wid] = a; sh1[wid] = b; sh2[wid] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0, tc = 0.0;
+        for (int w = 0; w < nw; ++w) { ta += sh0[w]; tb += sh1[w]; tc = fmax(tc, sh2[w]); }
+        out[0] = ta; out[1] = tb; out[2] = tc;
+        *ticket = 0u;  // ready for the next launch
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused Manakov nonlinear pass (the kernel the HBM-roofline target is quoted on).
+//   FIRST = true  : start of a step.  Ec is the step-start field, so φ = (8/9)γ·P
+//                   (channels.py:388-390 with Ex_conv == Ech_x) ; Pch is written.
+//                   Reads Ehd(16)+Ec(16), writes out(16)+Pch(4) bytes per 2-pol sample.
+//   FIRST = false : after a second half-step.  Accumulates the convergence sums
+//                   Σ|Efd-Ec|², Σ|Ec|² (channels.py:517-519) and max|Efd|² (for the next
+//                   adaptive step), forms φ = (8/9)γ(Pch+|Efd_x|²+|Efd_y|²)/2 (channels.py:436,493)
+//                   and writes the next rotated field out = Ehd·exp(j·dir·φ·hz) (channels.py:414-417).
+//                   Reads Efd(16)+Ec(16)+Ehd(16)+Pch(4), writes out(16): 68 B per 2-pol sample.
+// cphi = dir * hz * (8/9)γ  (FIRST)   or   dir * hz * (8/9)γ / 2  (!FIRST)
+// ------------------------------------------------------------------------------------------
+template <bool FIRST, int VEC>
+__global__ void __launch_bounds__(256)
+k_manakov_nl(const float2* __restrict__ Ehd, const float2* __restrict__ Efd,
+             const float2* __restrict__ Ec, float* __restrict__ Pch, float2* __restrict__ out,
+             int64_t N, int K, float cphi, double* __restrict__ partials,
+             double* __restrict__ sums, unsigned* __restrict__ ticket) {
+    const int64_t per_row = N / VEC;
+    const int64_t total = per_row * K;
+    const int64_t ystride = (int64_t)K * N;  // y row of pair p is row K+p
+    float s_num = 0.f, s_den = 0.f, s_max = 0.f;
+
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t off = (i / per_row) * N + (i % per_row) * VEC;  // pair row p, sample n
+        float2 hx[VEC], hy[VEC], cx[VEC], cy[VEC], fx[VEC], fy[VEC];
+        float pc[VEC];
+        if (VEC == 2) {
+            float4 t;
+            t = ldg4(Ehd + off);           hx[0] = make_float2(t.x, t.y); hx[1] = make_float2(t.z, t.w);
+            t = ldg4(Ehd + off + ystride); hy[0] = make_float2(t.x, t.y); hy[1] = make_float2(t.z, t.w);
+            t = ldg4(Ec + off);            cx[0] = make_float2(t.x, t.y); cx[1] = make_float2(t.z, t.w);
+            t = ldg4(Ec + off + ystride);  cy[0] = make_float2(t.x, t.y); cy[1] = make_float2(t.z, t.w);
+            if (!FIRST) {
+                t = ldg4(Efd + off);           fx[0] = make_float2(t.x, t.y); fx[1] = make_float2(t.z, t.w);
+                t = ldg4(Efd + off + ystride); fy[0] = make_float2(t.x, t.y); fy[1] = make_float2(t.z, t.w);
+                float2 p2 = __ldg(reinterpret_cast<const float2*>(Pch + off));
+                pc[0] = p2.x; pc[1] = p2.y;
+            }
+        } else {
+            hx[0] = __ldg(Ehd + off); hy[0] = __ldg(Ehd + off + ystride);
+            cx[0] = __ldg(Ec + off);  cy[0] = __ldg(Ec + off + ystride);
+            if (!FIRST) {
+                fx[0] = __ldg(Efd + off); fy[0] = __ldg(Efd + off + ystride);
+                pc[0] = __ldg(Pch + off);
+            }
+        }
+        float2 ox[VEC], oy[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float ph;
+            if (FIRST) {
+                float P = cabs2(cx[v]) + cabs2(cy[v]);
+                pc[v] = P;
+                ph = cphi * P;
+            } else {
+                float2 dx = make_float2(fx[v].x - cx[v].x, fx[v].y - cx[v].y);
+                float2 dy = make_float2(fy[v].x - cy[v].x, fy[v].y - cy[v].y);
+                s_num += cabs2(dx) + cabs2(dy);
+                s_den += cabs2(cx[v]) + cabs2(cy[v]);
+                float Pf = cabs2(fx[v]) + cabs2(fy[v]);
+                s_max = fmaxf(s_max, Pf);
+                ph = cphi * (pc[v] + Pf);
+            }
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            float2 rot = make_float2(cs, sn);
+            ox[v] = cmul(hx[v], rot);
+            oy[v] = cmul(hy[v], rot);
+        }
+        if (VEC == 2) {
+            stg4(out + off, make_float4(ox[0].x, ox[0].y, ox[1].x, ox[1].y));
+            stg4(out + off + ystride, make_float4(oy[0].x, oy[0].y, oy[1].x, oy[1].y));
+            if (FIRST) *reinterpret_cast<float2*>(Pch + off) = make_float2(pc[0], pc[1]);
+        } else {
+            out[off] = ox[0];
+            out[off + ystride] = oy[0];
+            if (FIRST) Pch[off] = pc[0];
+        }
+    }
+    if (!FIRST) block_reduce3_finalize(s_num, s_den, s_max, partials, sums, ticket);
+}
+
+// max over samples of |Ex|²+|Ey|² (adaptive step at span start; channels.py:394) and Σ power
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_power_stats(const float2* __restrict__ E, int64_t N, int K, double* __restrict__ partials,
+              double* __restrict__ sums, unsigned* __restrict__ ticket) {
+    const int64_t per_row = N / VEC;
+    const int64_t total = per_row * K;
+    const int64_t ystride = (int64_t)K * N;
+    float s_pow = 0.f, s_max = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t off = (i / per_row) * N + (i % per_row) * VEC;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float P = cabs2(__ldg(E + off + v)) + cabs2(__ldg(E + off + ystride + v));
+            s_pow += P;
+            s_max = fmaxf(s_max, P);
+        }
+    }
+    block_reduce3_finalize(0.f, s_pow, s_max, partials, sums, ticket);
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator + Box-Muller (EDFA ASE noise, devices.py:722-726).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float2 gauss_pair(uint32_t a, uint32_t b) {
+    float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+    float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+
+// E[r][n] = E[r][n]*g + noise     (gain-only when sigma == 0 and noise == nullptr)
+//   injected: noise[(r % noise_rows)][n]  — same realisation for x and y rows, every span
+//   philox  : CN(0, 2σ²) with counter (n, r, stream_id)
+__global__ void k_amp(float2* __restrict__ E, int R, int64_t N, float g, float sigma,
+                      const float2* __restrict__ noise, int noise_rows, uint64_t seed,
+                      uint64_t stream_id) {
+    const int64_t total = (int64_t)R * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float2 e = E[i];
+        e.x *= g; e.y *= g;
+        if (noise) {
+            int64_t r = i / N, n = i % N;
+            float2 w = __ldg(noise + (r % noise_rows) * N + n);
+            e.x += w.x; e.y += w.y;
+        } else if (sigma > 0.f) {
+            uint4 c = make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)stream_id,
+                                 (uint32_t)(stream_id >> 32));
+            uint4 rnd = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            float2 w = gauss_pair(rnd.x, rnd.y);
+            e.x = fmaf(sigma, w.x, e.x); e.y = fmaf(sigma, w.y, e.y);
+        }
+        E[i] = e;
+    }
+}
+
+// scalar NLSE nonlinear step: E *= exp(j c |E|²), c = γ·hz   (channels.py:225)
+template <int VEC>
+__global__ void k_nlse_phase(float2* __restrict__ E, int64_t total, float c) {
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * VEC; i < total;
+         i += (int64_t)gridDim.x * blockDim.x * VEC) {
+        float2 e[VEC];
+        if (VEC == 2) {
+            float4 t = *reinterpret_cast<const float4*>(E + i);
+            e[0] = make_float2(t.x, t.y); e[1] = make_float2(t.z, t.w);
+        } else e[0] = E[i];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float s, cs;
+            sincosf(c * cabs2(e[v]), &s, &cs);
+            e[v] = cmul(e[v], make_float2(cs, s));
+        }
+        if (VEC == 2) stg4(E + i, make_float4(e[0].x, e[0].y, e[1].x, e[1].y));
+        else E[i] = e[0];
+    }
+}
+
+// (N, C) interleaved columns (complex64 | complex128)  ->  planar rows[C][N] complex64
+template <typename TIN>
+__global__ void k_pack(const TIN* __restrict__ src, float2* __restrict__ rows, int64_t N, int C,
+                       int pairs) {
+    const int64_t total = N * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = i / C;
+        int c = (int)(i % C);
+        int r = pairs ? ((c & 1) * (C / 2) + (c >> 1)) : c;
+        TIN v = src[i];
+        rows[(int64_t)r * N + n] = make_float2((float)v.x, (float)v.y);
+    }
+}
+template <typename TOUT>
+__global__ void k_unpack(const float2* __restrict__ rows, TOUT* __restrict__ dst, int64_t N, int C,
+                         int pairs) {
+    const int64_t total = N * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = i / C;
+        int c = (int)(i % C);
+        int r = pairs ? ((c & 1) * (C / 2) + (c >> 1)) : c;
+        float2 v = rows[(int64_t)r * N + n];
+        TOUT o; o.x = v.x; o.y = v.y;
+        dst[i] = o;
+    }
+}
+
+}  // namespace ocb

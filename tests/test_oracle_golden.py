@@ -1,0 +1,155 @@
+"""Pin the CPU oracle (oracle/) against vectors produced by the unmodified reference.
+
+CPU-only.  Tolerances: the fiber oracle calls the same numpy FFT as the reference, so it must
+agree to rounding (1e-12); the equalizer oracle is complex128 while the reference is
+complex64+fastmath, so it agrees to the reference's own rounding noise (few 1e-6); BPS indices
+must be identical.
+"""
+import numpy as np
+import pytest
+
+from conftest import Bag, rel_l2
+from oracle import fiber_oracle as fo
+from oracle import rxdsp_oracle as ro
+
+
+def cfg(**kw):
+    return fo.FiberConfig(**kw)
+
+
+def test_ssfm_matches_reference(golden):
+    x = golden["ssfm_in"]
+    out = fo.nlse_ssfm(x, cfg(Fs=64e9, Ltotal=160, Lspan=80, hz=2.0, amp="ideal"))
+    assert rel_l2(out, golden["ssfm_ideal"]) < 1e-12
+    out = fo.nlse_ssfm(x, cfg(Fs=64e9, Ltotal=80, Lspan=80, hz=0.5, amp=None, gamma=2.0))
+    assert rel_l2(out, golden["ssfm_none"]) < 1e-12
+    out = fo.nlse_ssfm(x, cfg(Fs=64e9, Ltotal=80, Lspan=80, hz=4.0, amp="edfa", seed=7))
+    assert rel_l2(out, golden["ssfm_edfa_seed7"]) < 1e-12
+
+
+def test_manakov_fixed_step_matches_reference(golden):
+    st = {}
+    out = fo.manakov(golden["mk_in"], cfg(Fs=64e9, Ltotal=160, Lspan=80, hz=4.0, amp="ideal", nlprMethod=False), stats=st)
+    assert rel_l2(out, golden["mk_fixed_ideal"]) < 1e-12
+    assert [st["steps"], st["iterations"]] == list(golden["mk_fixed_ideal_counts"])
+
+
+def test_manakov_degenerate_last_step(golden):
+    """80/0.8 executes 101 loop steps in binary floating point."""
+    st = {}
+    out = fo.manakov(golden["mk_in"], cfg(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, amp=None, nlprMethod=False), stats=st)
+    assert rel_l2(out, golden["mk_fixed_degenerate"]) < 1e-12
+    assert [st["steps"], st["iterations"]] == list(golden["mk_fixed_degenerate_counts"])
+    assert st["steps"] == 101
+    assert len(fo.step_sizes_fixed(80, 0.8)) == 101
+    assert len(fo.step_sizes_fixed(80, 0.08)) == 1001
+    assert len(fo.step_sizes_fixed(80, 0.5)) == 160
+
+
+def test_manakov_adaptive_edfa_matches_reference(golden):
+    st = {}
+    out = fo.manakov(golden["mk_in"], cfg(Fs=64e9, Ltotal=40, Lspan=20, hz=0.5, amp="edfa", seed=11, nlprMethod=True,
+                                          maxNlinPhaseRot=2e-2, maxIter=5, saveSpanN=[2]), stats=st)
+    assert rel_l2(out, golden["mk_adaptive_edfa"]) < 1e-12
+    assert [st["steps"], st["iterations"]] == list(golden["mk_adaptive_edfa_counts"])
+
+
+def test_manakov_span_snapshots_and_k2(golden):
+    out = fo.manakov(golden["mk_in"], cfg(Fs=64e9, Ltotal=240, Lspan=80, hz=8.0, amp="ideal", nlprMethod=False,
+                                          saveSpanN=[1, 3]))
+    assert out.shape == golden["mk_savespans"].shape
+    assert rel_l2(out, golden["mk_savespans"]) < 1e-12
+    out = fo.manakov(golden["mk_in_k2"], cfg(Fs=64e9, Ltotal=80, Lspan=80, hz=4.0, amp="ideal", nlprMethod=False))
+    assert rel_l2(out, golden["mk_k2"]) < 1e-12
+    st = {}
+    out = fo.manakov(golden["mk_in_k2"], cfg(Fs=64e9, Ltotal=20, Lspan=20, hz=4.0, amp=None, nlprMethod=True), stats=st)
+    assert rel_l2(out, golden["mk_k2_adaptive"]) < 1e-12
+    assert [st["steps"], st["iterations"]] == list(golden["mk_k2_adaptive_counts"])
+
+
+def test_dbp_matches_reference(golden):
+    out = fo.manakov(golden["mk_fixed_ideal"], cfg(Fs=64e9, Ltotal=160, Lspan=80, hz=4.0, amp="ideal", nlprMethod=False),
+                     direction=-1)
+    assert rel_l2(out, golden["dbp_of_fixed_ideal"]) < 1e-12
+    # DBP of SSF with matched fixed steps returns the launch field (1.2e-9 on the reference)
+    assert rel_l2(out, golden["mk_in"]) < 1e-6
+    out = fo.manakov(golden["mk_in"], cfg(Fs=64e9, Ltotal=40, Lspan=20, hz=1.0, amp="edfa", nlprMethod=True,
+                                          maxNlinPhaseRot=1e-2), direction=-1)
+    assert rel_l2(out, golden["dbp_adaptive"]) < 1e-12
+
+
+def test_noise_stream_and_edfa(golden):
+    w = fo.legacy_noise((2, 64), 3.0e-7, 5)
+    assert np.array_equal(w, golden["noise_seed5"])  # numba's MT19937 stream == numpy RandomState, bit for bit
+    out = fo.edfa(golden["mk_in"][:256, 0], 16.0, 4.5, 193.1e12, 64e9, seed=9)
+    assert rel_l2(out, golden["edfa_seed9"]) < 1e-15
+
+
+def test_linear_limit_of_ssfm(golden):
+    """gamma=0 => ssfm equals one linear-fiber multiply (reference test tests/test_channels.py:155-180)."""
+    x = golden["ssfm_in"]
+    out = fo.nlse_ssfm(x, cfg(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, amp=None, gamma=0.0))
+    lin = fo.linear_fiber(x, 80, 0.2, 16, 193.1e12, 64e9)
+    assert np.max(np.abs(out - lin)) < 1e-12
+
+
+def test_edc_matches_reference(golden):
+    s = golden["edc_in"]
+    out = ro.edc(s, 100, 16, 193.1e12, 64e9, 32e9)
+    assert rel_l2(out, golden["edc_100km"]) < 1e-12
+    out = ro.edc(s[:, 0], 60, 17, 193.4e12, 64e9, 32e9, Nfft=256)
+    assert out.shape == golden["edc_1d_nfft256"].shape
+    assert rel_l2(out, golden["edc_1d_nfft256"]) < 1e-12
+    # overlap-save == direct linear convolution with the K taps, independent of the block size
+    h = ro.edc_taps(100, 16, 193.1e12, 64e9, 32e9)
+    assert rel_l2(ro.fir_direct(s[:, 1], h), golden["edc_100km"][:, 1]) < 1e-12
+    out64 = ro.edc(s.astype(np.complex64), 100, 16, 193.1e12, 64e9, 32e9)
+    assert out64.dtype == np.complex64
+    assert rel_l2(out64, golden["edc_c64"]) < 5e-6
+
+
+EQ_CASES = {
+    "cma_rde": dict(alg=["cma", "rde"], mu=[5e-3, 2e-3], L=[1000, 2000], numIter=2),
+    "nlms_ddlms": dict(alg=["nlms", "dd-lms"], mu=[5e-3, 1e-3], L=[800, 2200]),
+    "darde_rde": dict(alg=["da-rde", "rde"], mu=[5e-3, 2e-3], L=[600, 2400], numIter=3),
+    "cma_static_store": dict(alg=["cma", "static"], mu=[5e-3, 0.0], L=[2500, 500], storeCoeff=True),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(EQ_CASES))
+def test_equalizer_matches_reference(golden, tag):
+    kw = EQ_CASES[tag]
+    y, H, _, err, Hiter = ro.mimo_adapt_equalizer(golden["eq_in"], golden["eq_ref"], golden["const_qam16"],
+                                                   nTaps=15, SpS=2, **kw)
+    assert y.shape == golden[f"eq_{tag}_y"].shape
+    assert rel_l2(y, golden[f"eq_{tag}_y"]) < 2e-5
+    assert rel_l2(H, golden[f"eq_{tag}_H"]) < 2e-5
+    if "static" not in kw["alg"]:  # the reference reads uninitialised memory there
+        assert rel_l2(err, golden[f"eq_{tag}_err"].real) < 1e-4
+    assert Hiter.shape == golden[f"eq_{tag}_Hiter"].shape
+    assert rel_l2(Hiter, golden[f"eq_{tag}_Hiter"]) < 2e-5
+
+
+def test_equalizer_1d_input(golden):
+    y, *_ = ro.mimo_adapt_equalizer(golden["eq_in"][:, 0], None, golden["const_qam4"], nTaps=7, SpS=2, alg=["cma"],
+                                    mu=[2e-3])
+    assert rel_l2(y[:, 0], golden["eq_1d_y"]) < 2e-5
+
+
+def test_bps_indices_bit_exact(golden):
+    r, c = golden["bps_in"], golden["bps_const"]
+    ph, idx = ro.bps(r, 12, c, 64)
+    assert np.array_equal(ph, golden["bps_N12_B64"])
+    ph, idx = ro.bps(r, 0, c, 16)
+    assert np.array_equal(ph, golden["bps_N0_B16"])
+    ph, idx = ro.bps(r[:500], 5, golden["const_psk8"], 32)
+    assert np.array_equal(ph, golden["bps_N5_B32_psk"])
+
+
+def test_cpr_matches_reference(golden):
+    out, ph = ro.cpr_bps(golden["bps_in"], golden["const_qam16"], N=25, B=64, runFOE=False)
+    assert np.allclose(ph, golden["cpr_nofoe_ph"], atol=1e-12)
+    assert rel_l2(out, golden["cpr_nofoe_out"]) < 1e-12
+    out, ph = ro.cpr_bps(golden["cpr_foe_in"], golden["const_qam16"], N=35, B=64, runFOE=True, Ts=1 / 32e9)
+    assert np.allclose(ph, golden["cpr_foe_ph"], atol=1e-12)
+    assert rel_l2(out, golden["cpr_foe_out"]) < 1e-12
