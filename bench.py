@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: SSFM throughput in Msamples/s (2-pol, per
+span-step) on the cfg2 workload (11-ch WDM-like 2^20-sample dual-pol waveform, 10 x 80 km spans,
+hz = 0.08 km -> 1001 executed loop steps per span, fixed step, EDFA per span).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One bench "step" = one full propagation of one waveform (10 spans) per GPU.
+  value : N_samples x executed SSFM loop steps x n_gpus / time, input planar rows resident in HBM
+  e2e   : the same metric through the public drop-in call manakovSSF(numpy, param) -> numpy
+          (pinned host input, H2D + pack + run + unpack + D2H inside the timed region)
+  roofline     : the fused nonlinear iteration kernel, timed in situ with CUDA events
+  cpu_baseline : the CPU oracle port (numpy restatement of the reference) on a bounded sample
+Under torchrun every rank propagates its own independent realisation (weak scaling) and the final
+fields are gathered with one NCCL all_gather; time = max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES = 1 << 20
+FS = 512e9            # 32 GBd x 16 SpS
+N_CH, CH_SPACING = 11, 37.5e9
+P_CH_W = 10 ** (-2 / 10) * 1e-3  # -2 dBm per channel
+WORKLOAD = "cfg2: 11-ch WDM-like DP waveform, 2^20 samples, 10x80 km, hz=0.08 km (1001 steps/span), fixed step, amp=edfa"
+
+
+class Bag:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def channel_param(n_spans=10, **over):
+    p = Bag(Fs=FS, Ltotal=80 * n_spans, Lspan=80, hz=0.08, alpha=0.2, D=16, gamma=1.3, Fc=193.1e12,
+            amp="edfa", NF=4.5, maxIter=10, tol=1e-5, nlprMethod=False, maxNlinPhaseRot=2e-2, seed=456,
+            prgsBar=False, saveSpanN=[], returnParameters=False, prec=np.complex128)
+    p.__dict__.update(over)
+    return p
+
+
+def synth_waveform(seed, n=N_SAMPLES, dtype=np.complex128):
+    """Band-limited complex Gaussian (N, 2) occupying the 11 x 37.5 GHz WDM band, 11 x -2 dBm."""
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, 2)) + 1j * rng.normal(size=(n, 2))
+    f = np.fft.fftfreq(n) * FS
+    X[np.abs(f) > N_CH * CH_SPACING / 2] = 0
+    x = np.fft.ifft(X, axis=0)
+    x *= np.sqrt(N_CH * P_CH_W / np.mean(np.sum(np.abs(x) ** 2, axis=1)))
+    return np.ascontiguousarray(x.astype(dtype))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_oracle_rate(n_steps, n=N_SAMPLES, seed=0):
+    """Time the CPU oracle port on a bounded sample: n_steps fixed steps of the cfg2 fiber at full N."""
+    from oracle import fiber_oracle as fo
+    x = synth_waveform(seed, n)
+    cfg = fo.FiberConfig(Fs=FS, Ltotal=0.08 * n_steps, Lspan=0.08 * n_steps, hz=0.08, amp=None, nlprMethod=False)
+    st = {}
+    fo.manakov(x[:4096], fo.FiberConfig(Fs=FS, Ltotal=0.08, Lspan=0.08, hz=0.08, amp=None, nlprMethod=False))  # warm-up
+    t0 = time.perf_counter()
+    fo.manakov(x, cfg, stats=st)
+    dt = time.perf_counter() - t0
+    return n * st["steps"] / dt / 1e6, st["steps"], st["iterations"], dt
+
+
+def _cpu_worker(args):
+    n_steps, seed = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    return cpu_oracle_rate(n_steps, seed=seed)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, numpy pocketfft, one thread per
+    process like the reference) on all host cores, one independent realisation per process."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = min(os.cpu_count() or 1, 32)
+    steps_per_sample = 2
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            res = pool.map(_cpu_worker, [(steps_per_sample, 100 * it + i) for i in range(cores)])
+            dt = max(r[3] for r in res)  # slowest worker's propagation time (input synthesis excluded)
+            if it >= args.warmup:
+                times.append((dt, sum(r[1] for r in res)))
+    tot_t = sum(t for t, _ in times)
+    tot_steps = sum(s for _, s in times)
+    value = N_SAMPLES * tot_steps / tot_t / 1e6
+    sample = f"{steps_per_sample} SSFM steps at N=2^20 per process x {cores} processes per bench step"
+    print(json.dumps({
+        "impl": "reference", "metric": "SSFM Msamples/s (2-pol, per span-step)", "value": value, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "bounded_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spans", type=int, default=10, help="spans per propagation (10 = cfg2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from opticommpy_b200 import _cabi, _engine
+    from opticommpy_b200.channels import manakov_rows_device, manakovSSF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _cabi.lib()
+    st = C.c_void_p(_cabi.stream_ptr(torch))
+
+    prm = channel_param(args.spans)
+    # ---- inputs: one independent realisation per rank, pinned on the host, pristine copy in HBM
+    host = torch.empty((N_SAMPLES, 2), dtype=torch.complex128, pin_memory=True)
+    host_np = host.numpy()
+    host_np[...] = synth_waveform(1000 + rank)
+    d_raw = host.to("cuda", non_blocking=False)
+    rows0 = torch.empty((2, N_SAMPLES), dtype=torch.complex64, device="cuda")
+    _cabi.check(lib.ocb_pack_fields(C.c_void_p(d_raw.data_ptr()), _cabi.OCB_C128, N_SAMPLES, 2, 1,
+                                    C.c_void_p(rows0.data_ptr()), st), "pack")
+    rows = torch.empty_like(rows0)
+    gathered = [torch.empty_like(rows0) for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def one_step():
+        rows.copy_(rows0)
+        s = manakov_rows_device(rows, prm, +1)
+        if world > 1:
+            dist.all_gather(gathered, rows)  # the path's only collective: final gather over NVLink
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        stats = one_step()
+    barrier()
+    plan = _engine.get_plan(N_SAMPLES, 2)
+    _cabi.check(lib.ocb_ssfm_plan_profile(plan.handle, 1), "profile on")
+
+    # ---- timed region: device-resident
+    _cabi.launch_count_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot_ms, tot_steps, tot_iters = 0.0, 0, 0
+    with ClockSampler(local) as clk:
+        for _ in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations
+            barrier()
+            ev0.record()
+            stats = one_step()
+            ev1.record()
+            barrier()
+            tot_ms += ev0.elapsed_time(ev1)
+            tot_steps += stats["steps"]
+            tot_iters += stats["iterations"]
+    launches = _cabi.launch_count()
+    prof = (C.c_double * 6)()
+    _cabi.check(lib.ocb_ssfm_plan_profile_read(plan.handle, prof), "profile read")
+    _cabi.check(lib.ocb_ssfm_plan_profile(plan.handle, 0), "profile off")
+    t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms = float(t.item())
+    value = N_SAMPLES * tot_steps * world / (tot_ms * 1e-3) / 1e6
+
+    # ---- e2e: public drop-in API, numpy (pinned) in -> numpy out
+    e2e_t, e2e_steps = 0.0, 0
+    for i in range(1 + args.steps):
+        p2 = channel_param(args.spans)
+        barrier()
+        t0 = time.perf_counter()
+        out = manakovSSF(host_np, p2)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i > 0:  # first call warms the staging allocations
+            e2e_t += dt
+            e2e_steps += p2._b200_stats["steps"]
+    te = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = N_SAMPLES * e2e_steps * world / float(te.item()) / 1e6
+    noise_bytes = N_SAMPLES * 8  # injected ASE realisation (seeded reference mode)
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        mean_I = tot_iters / max(1, tot_steps)
+        nl_ms, nl_n = prof[0], prof[1]
+        bytes_nl = 68.0 * N_SAMPLES  # Efd 16 + Ec 16 + Ehd 16 + Pch 4 read, rotated field 16 written
+        ach = bytes_nl / (nl_ms / max(nl_n, 1) * 1e-3) / 1e9 if nl_n else None
+        step_bytes = (64.0 + 84.0 * mean_I) * N_SAMPLES  # SURVEY §8d model per SSFM step
+        step_ach = step_bytes * tot_steps / (tot_ms * 1e-3) / 1e9
+        line = {
+            "metric": "SSFM Msamples/s (2-pol, per span-step)", "value": value, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; f64 linear-operator phase)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "spans": args.spans, "ssfm_steps_per_bench_step": tot_steps // args.steps,
+                       "mean_fixed_point_iterations": mean_I, "l2": "256 MiB flush write between timed steps",
+                       "parallelism": f"{world} independent realisation(s), one per GPU, NCCL all_gather of the final field"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(host_np.nbytes + noise_bytes),
+                    "d2h_bytes_per_step": int(out.nbytes)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_manakov_nl<false,2> (fused NL pass: convergence sums + phase + rotation)",
+                         "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": (ach / peak) if ach else None, "traffic": None,
+                         "launches_timed": int(nl_n), "avg_us": 1e3 * nl_ms / max(nl_n, 1),
+                         "bytes_per_launch": bytes_nl},
+            "roofline_step": {"model": "64 + 84*I bytes per 2-pol sample-step", "achieved": step_ach, "peak": peak,
+                              "unit": "GB/s", "frac": step_ach / peak,
+                              "linear_half_step_avg_us": 1e3 * prof[4] / max(prof[5], 1),
+                              "nl_first_avg_us": 1e3 * prof[2] / max(prof[3], 1)},
+        }
+        if not args.no_cpu_baseline:
+            rate, s_, i_, dt = cpu_oracle_rate(6)
+            line["cpu_baseline"] = {"value": rate, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                                    "sample": f"{s_} fixed SSFM steps ({i_} iterations) of the same fiber at N=2^20, {dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,11 @@ int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out);
 int64_t ocb_ssfm_plan_workspace_bytes(const ocb_ssfm_plan* plan);
 int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* plan, void* dev_ptr, int64_t bytes);
 int ocb_ssfm_plan_destroy(ocb_ssfm_plan* plan);
+/* In-situ kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+ * kinds: 0 = fused nonlinear iteration pass, 1 = nonlinear first pass, 2 = linear half step
+ * (fft + multiply + ifft).  profile_read: out6[2k] = summed ms, out6[2k+1] = launches, then reset. */
+int ocb_ssfm_plan_profile(ocb_ssfm_plan* plan, int enable);
+int ocb_ssfm_plan_profile_read(ocb_ssfm_plan* plan, double* out6);
 
 /* ---- layout conversion ---------------------------------------------------------------
  * (N, C) interleaved-column host/device array <-> planar rows[C][N] complex64.

@@ -64,6 +64,19 @@ def _noise_setup(amp, seed, shape, noise_var, noiseRNG):
     return _cabi.NOISE_PHILOX, None, key & 0xFFFFFFFFFFFFFFFF
 
 
+def _manakov_params(param, direction, Nspans, n_save, *, alpha_lin, beta2, Fs, noise_var, gain_lin,
+                    noise_mode, key):
+    amp = param.amp
+    amp_mode = _AMP[amp] if amp in _AMP else _cabi.AMP_NONE  # unknown strings: no amplification, like the reference
+    return _cabi.ManakovParams(
+        alpha_lin=alpha_lin, beta2=beta2, gamma=float(param.gamma), Fs=float(Fs), Lspan=float(param.Lspan),
+        hz=float(param.hz), maxNlinPhaseRot=float(param.maxNlinPhaseRot), tol=float(param.tol),
+        n_spans=Nspans, maxIter=int(param.maxIter), nlprMethod=int(bool(param.nlprMethod)),
+        direction=direction, amp_mode=amp_mode, noise_mode=noise_mode, edfa_gain_lin=gain_lin,
+        edfa_noise_var=noise_var, seed=key, n_save=n_save, reserved=0,
+    )
+
+
 def _manakov_engine(Ei, param, direction, *, alpha_lin, beta2, Fs, noise_var=0.0, gain_lin=1.0):
     """Shared host driver of manakovSSF (direction=+1) and manakovDBP (direction=-1)."""
     torch = _cabi.require_cuda()
@@ -85,23 +98,12 @@ def _manakov_engine(Ei, param, direction, *, alpha_lin, beta2, Fs, noise_var=0.0
     if out_dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
         out_dtype = np.dtype(np.complex128)
 
-    amp = param.amp
-    if amp not in _AMP:
-        amp_mode = _cabi.AMP_NONE  # the reference silently applies no amplification
-    else:
-        amp_mode = _AMP[amp]
     noise_mode, noise_host, key = (_cabi.NOISE_PHILOX, None, 0)
     if direction > 0:
-        noise_mode, noise_host, key = _noise_setup(amp, getattr(param, "seed", None), (K, N), noise_var,
+        noise_mode, noise_host, key = _noise_setup(param.amp, getattr(param, "seed", None), (K, N), noise_var,
                                                    getattr(param, "noiseRNG", "reference"))
-
-    q = _cabi.ManakovParams(
-        alpha_lin=alpha_lin, beta2=beta2, gamma=float(param.gamma), Fs=float(Fs), Lspan=float(param.Lspan),
-        hz=float(param.hz), maxNlinPhaseRot=float(param.maxNlinPhaseRot), tol=float(param.tol),
-        n_spans=Nspans, maxIter=int(param.maxIter), nlprMethod=int(bool(param.nlprMethod)),
-        direction=direction, amp_mode=amp_mode, noise_mode=noise_mode, edfa_gain_lin=gain_lin,
-        edfa_noise_var=noise_var, seed=key, n_save=len(hits), reserved=0,
-    )
+    q = _manakov_params(param, direction, Nspans, len(hits), alpha_lin=alpha_lin, beta2=beta2, Fs=Fs,
+                        noise_var=noise_var, gain_lin=gain_lin, noise_mode=noise_mode, key=key)
     stats = _cabi.ManakovStats()
     plan = _engine.get_plan(N, 2 * K)
     nblk = max(1, len(hits))
@@ -132,6 +134,37 @@ def _manakov_engine(Ei, param, direction, *, alpha_lin, beta2, Fs, noise_var=0.0
         if Ech.dtype != Ei.dtype and np.iscomplexobj(Ei):
             Ech = Ech.astype(Ei.dtype)
     return Ech
+
+
+def manakov_rows_device(rows, param, direction=+1, noise_rows=None):
+    """Device-resident entry: propagate planar ``rows`` (torch complex64 CUDA tensor of shape (2K, N):
+    x rows then y rows) IN PLACE through ``ocb_manakov_run`` with the final field only (no snapshots).
+    ``param`` needs the same attributes as manakovSSF / manakovDBP (no defaults are filled in here).
+    Used by the sharded drivers and by bench.py's HBM-resident timing.  Returns the stats dict."""
+    torch = _cabi.require_cuda()
+    lib = _cabi.lib()
+    if rows.dtype != torch.complex64 or not rows.is_cuda or not rows.is_contiguous() or rows.dim() != 2:
+        raise TypeError("rows must be a contiguous CUDA complex64 tensor of shape (2K, N)")
+    R, N = rows.shape
+    alpha_lin, beta2 = _fiber_constants(param.alpha, param.D, param.Fc)
+    gain_lin, noise_var = 1.0, 0.0
+    if direction > 0 and param.amp == "edfa":
+        gain_lin, noise_var = _edfa_numbers(param.alpha * param.Lspan, param.NF, param.Fc, param.Fs)
+    noise_mode = _cabi.NOISE_INJECTED if noise_rows is not None else _cabi.NOISE_PHILOX
+    key = int(getattr(param, "seed", None) or 0) & 0xFFFFFFFFFFFFFFFF
+    Nspans = int(np.floor(param.Ltotal / param.Lspan))
+    q = _manakov_params(param, direction, Nspans, 0, alpha_lin=alpha_lin, beta2=beta2, Fs=param.Fs,
+                        noise_var=noise_var, gain_lin=gain_lin, noise_mode=noise_mode, key=key)
+    stats = _cabi.ManakovStats()
+    plan = _engine.get_plan(N, R, rows.device.index)
+    _cabi.check(
+        lib.ocb_manakov_run(plan.handle, C.c_void_p(rows.data_ptr()), C.byref(q),
+                            C.c_void_p(noise_rows.data_ptr()) if noise_rows is not None else None,
+                            None, None, C.byref(stats), C.c_void_p(_cabi.stream_ptr(torch))),
+        "ocb_manakov_run",
+    )
+    return {"steps": int(stats.steps), "iterations": int(stats.iterations), "nonconverged": int(stats.nonconverged),
+            "last_lim": float(stats.last_lim)}
 
 
 def manakovSSF(Ei, param):

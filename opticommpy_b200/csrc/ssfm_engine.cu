@@ -54,7 +54,26 @@ struct ocb_ssfm_plan {
     int max_blocks = kNumSMs * 8;
     // table cache keys
     double t1_h = NAN, t1_a = NAN, t1_b = NAN, t1_scale = NAN;
+    // optional in-situ kernel timing (CUDA events on the launching stream); kinds:
+    // 0 = fused NL iteration pass, 1 = NL first pass, 2 = linear half step (fft + multiply + ifft)
+    bool prof_on = false;
+    static constexpr int kProfKinds = 3, kProfCap = 2048;
+    std::vector<cudaEvent_t> prof_ev[kProfKinds];
+    int prof_n[kProfKinds] = {0, 0, 0};
 };
+
+namespace {
+struct ProfScope {  // records an event pair around the launches issued while it is alive
+    ocb_ssfm_plan* p; int kind; cudaStream_t st; bool active;
+    ProfScope(ocb_ssfm_plan* p_, int kind_, cudaStream_t st_) : p(p_), kind(kind_), st(st_) {
+        active = p->prof_on && p->prof_n[kind] < ocb_ssfm_plan::kProfCap;
+        if (active) cudaEventRecord(p->prof_ev[kind][2 * p->prof_n[kind]], st);
+    }
+    ~ProfScope() {
+        if (active) { cudaEventRecord(p->prof_ev[kind][2 * p->prof_n[kind] + 1], st); p->prof_n[kind]++; }
+    }
+};
+}  // namespace
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -123,8 +142,41 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
     return 0;
 }
 
+extern "C" int ocb_ssfm_plan_profile(ocb_ssfm_plan* p, int enable) {
+    OCB_REQUIRE(p != nullptr, "plan_profile: NULL plan");
+    if (enable && p->prof_ev[0].empty()) {
+        for (int k = 0; k < ocb_ssfm_plan::kProfKinds; ++k) {
+            p->prof_ev[k].resize(2 * ocb_ssfm_plan::kProfCap);
+            for (auto& e : p->prof_ev[k]) OCB_CUDA(cudaEventCreate(&e));
+        }
+    }
+    p->prof_on = enable != 0;
+    for (int k = 0; k < ocb_ssfm_plan::kProfKinds; ++k) p->prof_n[k] = 0;
+    return 0;
+}
+
+// out[2k] = summed duration [ms] of the recorded launches of kind k, out[2k+1] = their count
+extern "C" int ocb_ssfm_plan_profile_read(ocb_ssfm_plan* p, double* out6) {
+    OCB_REQUIRE(p && out6, "plan_profile_read: NULL argument");
+    OCB_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < ocb_ssfm_plan::kProfKinds; ++k) {
+        double tot = 0.0;
+        for (int i = 0; i < p->prof_n[k]; ++i) {
+            float ms = 0.f;
+            OCB_CUDA(cudaEventElapsedTime(&ms, p->prof_ev[k][2 * i], p->prof_ev[k][2 * i + 1]));
+            tot += ms;
+        }
+        out6[2 * k] = tot;
+        out6[2 * k + 1] = (double)p->prof_n[k];
+        p->prof_n[k] = 0;
+    }
+    return 0;
+}
+
 extern "C" int ocb_ssfm_plan_destroy(ocb_ssfm_plan* p) {
     if (!p) return 0;
+    for (int k = 0; k < ocb_ssfm_plan::kProfKinds; ++k)
+        for (auto& e : p->prof_ev[k]) cudaEventDestroy(e);
     if (p->fft_ok) cufftDestroy(p->fft);
     if (p->h_sums) cudaFreeHost(p->h_sums);
     if (p->stage_dev) cudaFree(p->stage_dev);
@@ -298,21 +350,33 @@ extern "C" int ocb_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_man
                 table_h = hz_;
             }
             // first half step: Ehd = ifft(fft(E)·L)    (channels.py:409-410)
-            OCB_CUFFT(cufftExecC2C(p->fft, bufs[cur], p->G, CUFFT_FORWARD));
-            if (launch_mul(p, p->G, p->T1, st)) return 1;
-            OCB_CUFFT(cufftExecC2C(p->fft, p->G, p->Ehd, CUFFT_INVERSE));
+            {
+                ProfScope ps(p, 2, st);
+                OCB_CUFFT(cufftExecC2C(p->fft, bufs[cur], p->G, CUFFT_FORWARD));
+                if (launch_mul(p, p->G, p->T1, st)) return 1;
+                OCB_CUFFT(cufftExecC2C(p->fft, p->G, p->Ehd, CUFFT_INVERSE));
+            }
 
             int ec = cur, dst = (cur + 1) % 3;
             const float c_first = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma);
             const float c_iter = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma * 0.5);
-            if (launch_nl(p, true, p->Ehd, nullptr, bufs[ec], p->Pch, p->G, N, K, c_first, nullptr, nullptr, nullptr, st)) return 1;
+            {
+                ProfScope ps(p, 1, st);
+                if (launch_nl(p, true, p->Ehd, nullptr, bufs[ec], p->Pch, p->G, N, K, c_first, nullptr, nullptr, nullptr, st)) return 1;
+            }
             for (int it = 0; it < q->maxIter; ++it) {  // channels.py:413
                 // second half step on the rotated field  (channels.py:420-421)
-                OCB_CUFFT(cufftExecC2C(p->fft, p->G, p->G, CUFFT_FORWARD));
-                if (launch_mul(p, p->G, p->T1, st)) return 1;
-                OCB_CUFFT(cufftExecC2C(p->fft, p->G, bufs[dst], CUFFT_INVERSE));
+                {
+                    ProfScope ps(p, 2, st);
+                    OCB_CUFFT(cufftExecC2C(p->fft, p->G, p->G, CUFFT_FORWARD));
+                    if (launch_mul(p, p->G, p->T1, st)) return 1;
+                    OCB_CUFFT(cufftExecC2C(p->fft, p->G, bufs[dst], CUFFT_INVERSE));
+                }
                 // convergence sums + speculative next rotation in one pass (channels.py:424, 436, 414-417)
-                if (launch_nl(p, false, p->Ehd, bufs[dst], bufs[ec], p->Pch, p->G, N, K, c_iter, p->partials, p->sums, p->ticket, st)) return 1;
+                {
+                    ProfScope ps(p, 0, st);
+                    if (launch_nl(p, false, p->Ehd, bufs[dst], bufs[ec], p->Pch, p->G, N, K, c_iter, p->partials, p->sums, p->ticket, st)) return 1;
+                }
                 if (fetch_sums(p, st)) return 1;
                 const double lim = sqrt(p->h_sums[0]) / sqrt(p->h_sums[1]);  // channels.py:517-519
                 S.iterations++;

@@ -1,0 +1,196 @@
+"""GPU parity of the split-step propagators: CUDA path (through the C-ABI / Python mirrors) vs
+the reference's golden vectors and vs the CPU oracle on seeded inputs.
+
+Tolerances (complex64 compute vs the reference's complex128): relative L2
+  1e-5 .. 1e-4 for <= 200 steps; step / iteration COUNTS must equal the reference's.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import Bag, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from opticommpy_b200 import _cabi
+    _cabi.require_cuda()
+    from opticommpy_b200 import channels, equalization
+    return Bag(ssfm=channels.ssfm, manakovSSF=channels.manakovSSF, manakovDBP=equalization.manakovDBP, cabi=_cabi)
+
+
+def test_ssfm_golden(api, golden):
+    x = golden["ssfm_in"]
+    out = api.ssfm(x, Bag(Fs=64e9, Ltotal=160, Lspan=80, hz=2.0, amp="ideal", prgsBar=False))
+    assert out.shape == x.shape and out.dtype == x.dtype
+    assert rel_l2(out, golden["ssfm_ideal"]) < 2e-5
+    out = api.ssfm(x, Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=0.5, amp=None, gamma=2.0, prgsBar=False))
+    assert rel_l2(out, golden["ssfm_none"]) < 5e-5
+    out = api.ssfm(x, Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=4.0, amp="edfa", seed=7, prgsBar=False))
+    assert rel_l2(out, golden["ssfm_edfa_seed7"]) < 2e-5
+
+
+def test_ssfm_reference_invariants(api, golden):
+    """The reference's own TestSSFM invariants (tests/test_channels.py:155-224)."""
+    from oracle import fiber_oracle as fo
+    x = golden["ssfm_in"]
+    p = Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, alpha=0.2, D=16, gamma=0.0, Fc=193.1e12, amp=None, prgsBar=False)
+    lin = fo.linear_fiber(x, 80, 0.2, 16, 193.1e12, 64e9)
+    out = api.ssfm(x, p)
+    assert rel_l2(out, lin) < 1e-5  # gamma = 0 -> linear channel (atol 1e-12 in float64; 1e-5 rel. in complex64)
+    p2 = Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, alpha=0.0, gamma=1.3, amp=None, prgsBar=False)
+    out = api.ssfm(x, p2)
+    assert np.sum(np.abs(out) ** 2) == pytest.approx(np.sum(np.abs(x) ** 2), rel=1e-5)  # power conserved
+    assert rel_l2(np.abs(np.fft.fft(out)), np.abs(np.fft.fft(x))) > 1e-3  # nonlinearity changes the spectrum
+    # defaults are written back into param, like the reference (channels.py:158-170)
+    assert p.Ltotal == 80 and p.NF == 4.5 and p.prec == np.complex128 and p.returnParameters is False
+
+
+def test_manakov_fixed_golden(api, golden):
+    p = Bag(Fs=64e9, Ltotal=160, Lspan=80, hz=4.0, amp="ideal", nlprMethod=False, saveSpanN=[], prgsBar=False)
+    out = api.manakovSSF(golden["mk_in"], p)
+    assert out.shape == golden["mk_fixed_ideal"].shape and out.dtype == np.complex128
+    assert rel_l2(out, golden["mk_fixed_ideal"]) < 5e-5
+    assert [p._b200_stats["steps"], p._b200_stats["iterations"]] == list(golden["mk_fixed_ideal_counts"])
+
+
+def test_manakov_degenerate_last_step(api, golden):
+    p = Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, amp=None, nlprMethod=False, saveSpanN=[], prgsBar=False)
+    out = api.manakovSSF(golden["mk_in"], p)
+    assert rel_l2(out, golden["mk_fixed_degenerate"]) < 1e-4
+    assert p._b200_stats["steps"] == 101  # float-accumulated z
+    assert p._b200_stats["iterations"] == int(golden["mk_fixed_degenerate_counts"][1])
+
+
+def test_manakov_adaptive_edfa_golden(api, golden):
+    p = Bag(Fs=64e9, Ltotal=40, Lspan=20, hz=0.5, amp="edfa", seed=11, nlprMethod=True, maxNlinPhaseRot=2e-2,
+            maxIter=5, prgsBar=False)
+    out, pr = api.manakovSSF(golden["mk_in"], Bag(**{**p.__dict__, "returnParameters": True}))
+    assert pr.saveSpanN == [2]  # default written back: Ltotal // Lspan
+    assert out.shape == golden["mk_adaptive_edfa"].shape
+    assert rel_l2(out, golden["mk_adaptive_edfa"]) < 1e-4
+    assert [pr._b200_stats["steps"], pr._b200_stats["iterations"]] == list(golden["mk_adaptive_edfa_counts"])
+
+
+def test_manakov_snapshots_and_k2(api, golden):
+    p = Bag(Fs=64e9, Ltotal=240, Lspan=80, hz=8.0, amp="ideal", nlprMethod=False, saveSpanN=[1, 3], prgsBar=False)
+    out = api.manakovSSF(golden["mk_in"], p)
+    assert out.shape == golden["mk_savespans"].shape
+    assert rel_l2(out, golden["mk_savespans"]) < 5e-5
+    p = Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=4.0, amp="ideal", nlprMethod=False, saveSpanN=[], prgsBar=False)
+    out = api.manakovSSF(golden["mk_in_k2"], p)
+    assert rel_l2(out, golden["mk_k2"]) < 5e-5
+    p = Bag(Fs=64e9, Ltotal=20, Lspan=20, hz=4.0, amp=None, nlprMethod=True, saveSpanN=[], prgsBar=False)
+    out = api.manakovSSF(golden["mk_in_k2"], p)
+    assert rel_l2(out, golden["mk_k2_adaptive"]) < 1e-4
+    assert [p._b200_stats["steps"], p._b200_stats["iterations"]] == list(golden["mk_k2_adaptive_counts"])
+    with pytest.raises(ValueError):  # the reference breaks the same way for K>1 with snapshots (App. B #3)
+        api.manakovSSF(golden["mk_in_k2"], Bag(Fs=64e9, Ltotal=80, Lspan=80, prgsBar=False))
+
+
+def test_dbp_golden_and_round_trip(api, golden):
+    p = Bag(Fs=64e9, Ltotal=160, Lspan=80, hz=4.0, amp="ideal", nlprMethod=False, saveSpanN=[], prgsBar=False)
+    out = api.manakovDBP(golden["mk_fixed_ideal"], p)
+    assert rel_l2(out, golden["dbp_of_fixed_ideal"]) < 5e-5
+    p = Bag(Fs=64e9, Ltotal=40, Lspan=20, hz=1.0, amp="edfa", nlprMethod=True, maxNlinPhaseRot=1e-2, saveSpanN=[],
+            prgsBar=False)
+    out = api.manakovDBP(golden["mk_in"], p)
+    assert rel_l2(out, golden["dbp_adaptive"]) < 1e-4
+    # manakovDBP(manakovSSF(x)) == x with matched fixed steps, full GPU round trip at 2^16
+    rng = np.random.default_rng(3)
+    x = (rng.normal(size=(1 << 16, 2)) + 1j * rng.normal(size=(1 << 16, 2))) * np.sqrt(1e-3)
+    f = Bag(Fs=64e9, Ltotal=160, Lspan=80, hz=2.0, amp="ideal", nlprMethod=False, saveSpanN=[], prgsBar=False)
+    y = api.manakovSSF(x, f)
+    b = Bag(Fs=64e9, Ltotal=160, Lspan=80, hz=2.0, amp="ideal", nlprMethod=False, saveSpanN=[], prgsBar=False)
+    xr = api.manakovDBP(y, b)
+    assert rel_l2(xr, x) < 2e-4
+
+
+def test_manakov_vs_oracle_seeded(api):
+    """cfg1-shaped case (BASELINE.json configs[0]): N=2^14 here so the oracle takes seconds."""
+    from oracle import fiber_oracle as fo
+    rng = np.random.default_rng(8)
+    n = 1 << 14
+    x = (rng.normal(size=(n, 2)) + 1j * rng.normal(size=(n, 2))) * np.sqrt(11 * 10 ** (-0.2) * 1e-3 / 4)
+    p = Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, alpha=0.2, D=16, gamma=1.3, Fc=193.1e12, amp=None,
+            nlprMethod=False, maxIter=10, tol=1e-5, saveSpanN=[], prgsBar=False)
+    st = {}
+    ref = fo.manakov(x, fo.FiberConfig(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, amp=None, nlprMethod=False), stats=st)
+    out = api.manakovSSF(x, p)
+    assert rel_l2(out, ref) < 1e-4
+    assert p._b200_stats["steps"] == st["steps"] == 101
+    assert p._b200_stats["iterations"] == st["iterations"]
+    # complex64 input is accepted and returned as complex64
+    out64 = api.manakovSSF(x.astype(np.complex64), Bag(**{k: v for k, v in p.__dict__.items() if k != "_b200_stats"}))
+    assert out64.dtype == np.complex64 and rel_l2(out64, ref) < 1e-4
+
+
+def test_nl_pass_unit(api):
+    """The fused nonlinear kernel alone vs the oracle's formulas (channels.py:414-417, 436, 517-519)."""
+    import torch
+    from oracle import fiber_oracle as fo
+    lib = api.cabi.lib()
+    rng = np.random.default_rng(1)
+    K, n = 2, 10000
+    def f():
+        return ((rng.normal(size=(2 * K, n)) + 1j * rng.normal(size=(2 * K, n))) * 0.05).astype(np.complex64)
+    Ehd, Ec, Efd = f(), f(), f()
+    Efd = (Ec + 1e-3 * Efd).astype(np.complex64)
+    d = lambda a: torch.from_numpy(a.view(np.float32).copy()).cuda()
+    dEhd, dEc, dEfd = d(Ehd), d(Ec), d(Efd)
+    dP = torch.zeros((K, n), dtype=torch.float32, device="cuda")
+    dout = torch.zeros_like(dEhd)
+    dsums = torch.zeros(3, dtype=torch.float64, device="cuda")
+    gamma, hz = 1.3, 0.7
+    vp = C.c_void_p
+    st = vp(api.cabi.stream_ptr(torch))
+    # first pass: phi = (8/9) gamma P, writes Pch
+    api.cabi.check(lib.ocb_manakov_nl_pass(vp(dEhd.data_ptr()), None, vp(dEc.data_ptr()), vp(dP.data_ptr()),
+                                           vp(dout.data_ptr()), None, n, K, gamma, hz, 1, st), "nl_pass first")
+    P = np.abs(Ec[:K].astype(np.complex128)) ** 2 + np.abs(Ec[K:].astype(np.complex128)) ** 2
+    assert np.allclose(dP.cpu().numpy(), P, rtol=1e-6)
+    ox, oy = fo.manakov_nl_pass(Ehd[:K], Ehd[K:], Ec[:K], Ec[K:], P, gamma, hz)
+    got = dout.cpu().numpy().view(np.complex64).reshape(2 * K, n)
+    assert rel_l2(got, np.concatenate([ox, oy])) < 1e-6
+    # iteration pass (DBP sign): sums + rotation with the trapezoidal phase
+    api.cabi.check(lib.ocb_manakov_nl_pass(vp(dEhd.data_ptr()), vp(dEfd.data_ptr()), vp(dEc.data_ptr()),
+                                           vp(dP.data_ptr()), vp(dout.data_ptr()), vp(dsums.data_ptr()), n, K, gamma,
+                                           hz, -1, st), "nl_pass iter")
+    ox, oy = fo.manakov_nl_pass(Ehd[:K], Ehd[K:], Efd[:K], Efd[K:], P, gamma, hz, direction=-1)
+    got = dout.cpu().numpy().view(np.complex64).reshape(2 * K, n)
+    assert rel_l2(got, np.concatenate([ox, oy])) < 1e-6
+    s = dsums.cpu().numpy()
+    E64 = lambda a: a.astype(np.complex128)
+    assert s[0] == pytest.approx(np.sum(np.abs(E64(Efd) - E64(Ec)) ** 2), rel=1e-5)
+    assert s[1] == pytest.approx(np.sum(np.abs(E64(Ec)) ** 2), rel=1e-5)
+    assert s[2] == pytest.approx(np.max(np.abs(E64(Efd[:K])) ** 2 + np.abs(E64(Efd[K:])) ** 2), rel=1e-5)
+
+
+def test_edfa_philox_statistics(api):
+    """amp='edfa' without a seed uses the on-device Philox stream: check gain, noise power, whiteness."""
+    import torch
+    lib = api.cabi.lib()
+    n, rows = 1 << 18, 2
+    x = torch.zeros((rows, n, 2), dtype=torch.float32, device="cuda")
+    x[..., 0] = 1.0
+    var = 4.5e-3
+    vp = C.c_void_p
+    api.cabi.check(lib.ocb_edfa_apply(vp(x.data_ptr()), rows, n, 4.0, var, api.cabi.NOISE_PHILOX, None, 0, 1234, 0,
+                                      vp(api.cabi.stream_ptr(torch))), "edfa_apply")
+    y = x.cpu().numpy().view(np.complex64).reshape(rows, n)
+    w = y - 2.0
+    assert np.mean(np.abs(w) ** 2) == pytest.approx(var, rel=0.02)
+    assert abs(np.mean(w)) < 5e-4
+    assert abs(np.mean(w.real * w.imag)) < var * 0.02
+    assert abs(np.vdot(w[0], w[1])) / n < var * 0.02  # rows are independent
+    assert abs(np.vdot(w[0, 1:], w[0, :-1])) / n < var * 0.02  # white
+
+
+def test_missing_fs_and_bad_amp(api, golden):
+    with pytest.raises(NameError):
+        api.manakovSSF(golden["mk_in"], Bag(Ltotal=80))
+    with pytest.raises(AssertionError):
+        api.manakovSSF(golden["mk_in"], Bag(Fs=64e9, NF=2.0, Ltotal=80, prgsBar=False))
