@@ -69,6 +69,15 @@ int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out);
 int64_t ocb_ssfm_plan_workspace_bytes(const ocb_ssfm_plan* plan);
 int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* plan, void* dev_ptr, int64_t bytes);
 int ocb_ssfm_plan_destroy(ocb_ssfm_plan* plan);
+/* Transform engine of a plan.  AUTO picks the fused four-step kernels (own FFT passes with the
+ * linear operator / Kerr rotation / convergence sums fused in) when N is a power of two in
+ * 2^16..2^20 and the plan holds one pol-pair (rows = 2) or one row; otherwise the cuFFT-driven
+ * engine (any N, any K).  Both engines implement the same reference loop. */
+#define OCB_ENGINE_AUTO 0
+#define OCB_ENGINE_CUFFT 1
+#define OCB_ENGINE_FUSED 2
+int ocb_ssfm_plan_set_engine(ocb_ssfm_plan* plan, int engine);
+int ocb_ssfm_plan_engine(const ocb_ssfm_plan* plan); /* engine a run would use now */
 /* In-situ kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
  * kinds: 0 = fused nonlinear iteration pass, 1 = nonlinear first pass, 2 = linear half step
  * (fft + multiply + ifft).  profile_read: out6[2k] = summed ms, out6[2k+1] = launches, then reset. */

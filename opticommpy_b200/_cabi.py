@@ -62,6 +62,8 @@ SIGNATURES = {
     "ocb_ssfm_plan_workspace_bytes": (_i64, [_vp]),
     "ocb_ssfm_plan_bind_workspace": (_i, [_vp, _vp, _i64]),
     "ocb_ssfm_plan_destroy": (_i, [_vp]),
+    "ocb_ssfm_plan_set_engine": (_i, [_vp, _i]),
+    "ocb_ssfm_plan_engine": (_i, [_vp]),
     "ocb_ssfm_plan_profile": (_i, [_vp, _i]),
     "ocb_ssfm_plan_profile_read": (_i, [_vp, C.POINTER(C.c_double)]),
     "ocb_pack_fields": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp]),

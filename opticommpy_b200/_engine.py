@@ -8,12 +8,26 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import _cabi
 
 _MAX_PLANS = 4
+ENGINES = {"auto": 0, "cufft": 1, "fused": 2}
+_default_engine = os.environ.get("OCB_ENGINE", "auto")
+
+
+def set_default_engine(name: str) -> None:
+    """'auto' (fused four-step kernels when N = 2^16..2^20 and K = 1, else cuFFT-driven),
+    'cufft' or 'fused'.  Both engines implement the same reference loop; this is a tuning /
+    cross-check switch, not a backend dispatch."""
+    global _default_engine
+    if name not in ENGINES:
+        raise ValueError(f"unknown engine {name!r}")
+    _default_engine = name
+    clear_plans()
 
 
 class SsfmPlan:
@@ -31,6 +45,8 @@ class SsfmPlan:
             aligned = (base + 255) // 256 * 256
             _cabi.check(self._lib.ocb_ssfm_plan_bind_workspace(h, C.c_void_p(aligned), nbytes),
                         "ocb_ssfm_plan_bind_workspace")
+            _cabi.check(self._lib.ocb_ssfm_plan_set_engine(h, ENGINES[_default_engine]), "ocb_ssfm_plan_set_engine")
+            self.engine = {1: "cufft", 2: "fused"}[int(self._lib.ocb_ssfm_plan_engine(h))]
 
     def close(self):
         if getattr(self, "handle", None):

@@ -11,6 +11,7 @@
 
 #include "../../include/opticomm_b200.h"
 #include "ssfm_kernels.cuh"
+#include "fused_kernels.cuh"
 
 using namespace ocb;
 
@@ -52,6 +53,11 @@ struct ocb_ssfm_plan {
     void* stage_dev = nullptr;
     int64_t stage_bytes = 0;
     int max_blocks = kNumSMs * 8;
+    // fused four-step engine (power-of-two N = (32 q1) x (32 q2), single pol-pair): geometry + tables
+    int engine = 0;       // OCB_ENGINE_*: 0 auto, 1 cuFFT, 2 fused
+    bool fused_ok = false, fused_tables_ready = false;
+    int q1 = 0, q2 = 0;
+    float2 *tw1 = nullptr, *tw2 = nullptr, *tabV = nullptr, *tabU = nullptr;
     // table cache keys
     double t1_h = NAN, t1_a = NAN, t1_b = NAN, t1_scale = NAN;
     // optional in-situ kernel timing (CUDA events on the launching stream); kinds:
@@ -77,6 +83,26 @@ struct ProfScope {  // records an event pair around the launches issued while it
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+static bool fused_geometry(int64_t N, int* q1, int* q2) {
+    if (N <= 0 || (N & (N - 1))) return false;
+    int n = 0;
+    while ((1ll << n) < N) ++n;
+    const int n1 = (n + 1) / 2, n2 = n / 2;  // N1 >= N2
+    if (n2 < 8 || n1 > 10) return false;      // 2^16 .. 2^20
+    *q1 = (1 << n1) / 32;
+    *q2 = (1 << n2) / 32;
+    return true;
+}
+static int64_t fused_table_bytes(const ocb_ssfm_plan* p) {
+    if (!p->fused_ok) return 0;
+    return align_up(32ll * p->q1 * 8, 256) + align_up(32ll * p->q2 * 8, 256) +
+           align_up(32ll * p->q2 * 32 * 8, 256) + align_up(32ll * p->q2 * p->q1 * 8, 256);
+}
+static int fused_manakov_run(ocb_ssfm_plan*, void*, const ocb_manakov_params*, const void*, const int32_t*, void*,
+                             ocb_manakov_stats*, cudaStream_t);
+static int fused_nlse_run(ocb_ssfm_plan*, void*, const ocb_nlse_params*, const void*, cudaStream_t);
+static bool use_fused(const ocb_ssfm_plan* p) { return p->fused_ok && p->engine != OCB_ENGINE_CUFFT; }
+
 extern "C" int ocb_abi_version(void) { return OCB_ABI_VERSION; }
 extern "C" const char* ocb_last_error(void) { return last_error().c_str(); }
 extern "C" int64_t ocb_launch_count(void) { return launch_counter(); }
@@ -89,6 +115,7 @@ extern "C" int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out) {
     ocb_ssfm_plan* p = new ocb_ssfm_plan();
     p->N = N;
     p->rows = rows;
+    p->fused_ok = (rows == 1 || rows == 2) && fused_geometry(N, &p->q1, &p->q2);
     if (cufftCreate(&p->fft) != CUFFT_SUCCESS) { delete p; return fail("cufftCreate failed", __FILE__, __LINE__); }
     p->fft_ok = true;
     if (cufftSetAutoAllocation(p->fft, 0) != CUFFT_SUCCESS) { ocb_ssfm_plan_destroy(p); return fail("cufftSetAutoAllocation failed", __FILE__, __LINE__); }
@@ -116,6 +143,7 @@ extern "C" int64_t ocb_ssfm_plan_workspace_bytes(const ocb_ssfm_plan* p) {
     b += align_up((int64_t)p->max_blocks * 3 * sizeof(double), 256);  // partials
     b += 256;                                                         // sums + ticket
     b += align_up((int64_t)p->fft_work, 256);
+    b += fused_table_bytes(p);
     return b;
 }
 
@@ -135,11 +163,31 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
     p->Pch = (float*)c; c += align_up(((int64_t)(p->rows + 1) / 2) * p->N * sizeof(float), 256);
     p->partials = (double*)c; c += align_up((int64_t)p->max_blocks * 3 * sizeof(double), 256);
     p->sums = (double*)c; p->ticket = (unsigned*)(c + 64); c += 256;
-    p->fft_area = c;
+    p->fft_area = c; c += align_up((int64_t)p->fft_work, 256);
     if (p->fft_work > 0) OCB_CUFFT(cufftSetWorkArea(p->fft, p->fft_area));
+    if (p->fused_ok) {
+        p->tw1 = (float2*)c; c += align_up(32ll * p->q1 * 8, 256);
+        p->tw2 = (float2*)c; c += align_up(32ll * p->q2 * 8, 256);
+        p->tabV = (float2*)c; c += align_up(32ll * p->q2 * 32 * 8, 256);
+        p->tabU = (float2*)c; c += align_up(32ll * p->q2 * p->q1 * 8, 256);
+        p->fused_tables_ready = false;
+    }
     OCB_CUDA(cudaMemset(p->sums, 0, 256));
     p->t1_h = NAN;
     return 0;
+}
+
+extern "C" int ocb_ssfm_plan_set_engine(ocb_ssfm_plan* p, int engine) {
+    OCB_REQUIRE(p != nullptr, "plan_set_engine: NULL plan");
+    OCB_REQUIRE(engine >= OCB_ENGINE_AUTO && engine <= OCB_ENGINE_FUSED, "plan_set_engine: unknown engine");
+    OCB_REQUIRE(engine != OCB_ENGINE_FUSED || p->fused_ok,
+                "plan_set_engine: the fused four-step engine needs N = 2^16..2^20 and a single pol-pair");
+    p->engine = engine;
+    return 0;
+}
+extern "C" int ocb_ssfm_plan_engine(const ocb_ssfm_plan* p) {
+    if (!p) return -1;
+    return use_fused(p) ? OCB_ENGINE_FUSED : OCB_ENGINE_CUFFT;
 }
 
 extern "C" int ocb_ssfm_plan_profile(ocb_ssfm_plan* p, int enable) {
@@ -307,6 +355,8 @@ extern "C" int ocb_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_man
     OCB_REQUIRE(q->n_save == 0 || (save_spans && save_dev), "manakov_run: snapshot buffers missing");
 
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_fused(p) && p->rows == 2)
+        return fused_manakov_run(p, rows_inout, q, noise_dev, save_spans, save_dev, stats, st);
     OCB_CUFFT(cufftSetStream(p->fft, st));
     const int64_t N = p->N;
     const int R = p->rows, K = R / 2;
@@ -472,6 +522,7 @@ extern "C" int ocb_nlse_run(ocb_ssfm_plan* p, void* row_inout, const ocb_nlse_pa
     if (q->amp_mode == OCB_AMP_EDFA && q->noise_mode == OCB_NOISE_INJECTED)
         OCB_REQUIRE(noise_dev != nullptr, "nlse_run: injected noise buffer missing");
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_fused(p) && p->rows == 1) return fused_nlse_run(p, row_inout, q, noise_dev, st);
     OCB_CUFFT(cufftSetStream(p->fft, st));
     const int64_t N = p->N;
     const int R = p->rows;
@@ -531,3 +582,5 @@ extern "C" int ocb_nlse_run_host(ocb_ssfm_plan* p, const void* Ei_host, int in_d
     OCB_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
+
+#include "fused_engine.inl"

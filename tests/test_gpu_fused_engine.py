@@ -1,0 +1,94 @@
+"""The fused four-step engine (own FFT passes, N = 2^16..2^20) vs the CPU oracle and vs the
+cuFFT-driven engine of the same library (identical loop, different transform kernels)."""
+import numpy as np
+import pytest
+
+from conftest import Bag, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from opticommpy_b200 import _cabi
+    _cabi.require_cuda()
+    from opticommpy_b200 import _engine, channels, equalization
+    yield Bag(ssfm=channels.ssfm, manakovSSF=channels.manakovSSF, manakovDBP=equalization.manakovDBP, eng=_engine)
+    _engine.set_default_engine("auto")
+
+
+def field(seed, n, cols, p_w):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, cols)) + 1j * rng.normal(size=(n, cols))
+    X[np.abs(np.fft.fftfreq(n)) > 0.3] = 0
+    x = np.fft.ifft(X, axis=0)
+    return x * np.sqrt(p_w / np.mean(np.sum(np.abs(x) ** 2, axis=1)))
+
+
+def both(api, fn, x, **kw):
+    out = {}
+    for name in ("fused", "cufft"):
+        api.eng.set_default_engine(name)
+        p = Bag(**kw)
+        out[name] = (fn(x, p), p)
+        assert api.eng.get_plan(x.shape[0], 1 if x.ndim == 1 else x.shape[1]).engine == name
+    api.eng.set_default_engine("auto")
+    return out
+
+
+def test_fused_manakov_cfg1_vs_oracle(api):
+    """BASELINE configs[0]: single-channel 2-pol manakovSSF, 2^16 samples, 1 span, hz=0.8 (101 steps)."""
+    from oracle import fiber_oracle as fo
+    x = field(8, 1 << 16, 2, 11 * 10 ** (-0.2) * 1e-3 / 2)
+    kw = dict(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, alpha=0.2, D=16, gamma=1.3, Fc=193.1e12, amp=None,
+              nlprMethod=False, maxIter=10, tol=1e-5, saveSpanN=[], prgsBar=False)
+    st = {}
+    ref = fo.manakov(x, fo.FiberConfig(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, amp=None, nlprMethod=False), stats=st)
+    r = both(api, api.manakovSSF, x, **kw)
+    for name, (out, p) in r.items():
+        assert rel_l2(out, ref) < 1e-4, name
+        assert p._b200_stats["steps"] == st["steps"] == 101, name
+        assert p._b200_stats["iterations"] == st["iterations"], name
+
+
+@pytest.mark.parametrize("n_log2", [16, 17, 18, 19, 20])
+def test_fused_equals_cufft_engine(api, n_log2):
+    """Every supported geometry (N1 x N2 = 256x256 ... 1024x1024), fixed and adaptive steps, edfa."""
+    n = 1 << n_log2
+    x = field(n_log2, n, 2, 6e-3)
+    r = both(api, api.manakovSSF, x, Fs=128e9, Ltotal=20, Lspan=10, hz=1.0, amp="edfa", seed=5, nlprMethod=False,
+             saveSpanN=[], prgsBar=False)
+    assert rel_l2(r["fused"][0], r["cufft"][0]) < 2e-5
+    assert r["fused"][1]._b200_stats == pytest.approx(r["cufft"][1]._b200_stats, rel=1e-2)
+    assert r["fused"][1]._b200_stats["iterations"] == r["cufft"][1]._b200_stats["iterations"]
+    r = both(api, api.manakovSSF, x, Fs=128e9, Ltotal=10, Lspan=10, hz=1.0, amp=None, nlprMethod=True,
+             maxNlinPhaseRot=2e-2, saveSpanN=[], prgsBar=False)
+    assert rel_l2(r["fused"][0], r["cufft"][0]) < 5e-5
+    assert abs(r["fused"][1]._b200_stats["steps"] - r["cufft"][1]._b200_stats["steps"]) <= 1
+
+
+def test_fused_dbp_round_trip_and_engines(api):
+    x = field(3, 1 << 18, 2, 4e-3)
+    kw = dict(Fs=64e9, Ltotal=160, Lspan=80, hz=4.0, amp="ideal", nlprMethod=False, saveSpanN=[], prgsBar=False)
+    y = both(api, api.manakovSSF, x, **kw)
+    b = both(api, api.manakovDBP, y["fused"][0], **kw)
+    assert rel_l2(b["fused"][0], b["cufft"][0]) < 1e-4  # two independent complex64 error paths, 80 steps
+    assert rel_l2(b["fused"][0], x) < 1e-4  # DBP(SSF(x)) == x with matched steps
+
+
+def test_fused_ssfm_vs_oracle_and_cufft(api):
+    from oracle import fiber_oracle as fo
+    x = field(1, 1 << 16, 1, 4e-3)[:, 0]
+    r = both(api, api.ssfm, x, Fs=64e9, Ltotal=160, Lspan=80, hz=1.0, amp="ideal", prgsBar=False)
+    ref = fo.nlse_ssfm(x, fo.FiberConfig(Fs=64e9, Ltotal=160, Lspan=80, hz=1.0, amp="ideal"))
+    assert rel_l2(r["fused"][0], ref) < 1e-4 and rel_l2(r["cufft"][0], ref) < 1e-4
+    r = both(api, api.ssfm, x, Fs=64e9, Ltotal=80, Lspan=80, hz=2.0, amp="edfa", seed=3, prgsBar=False)
+    ref = fo.nlse_ssfm(x, fo.FiberConfig(Fs=64e9, Ltotal=80, Lspan=80, hz=2.0, amp="edfa", seed=3))
+    assert rel_l2(r["fused"][0], ref) < 1e-4
+    # linear limit and power conservation (the reference's TestSSFM invariants) on the fused engine
+    api.eng.set_default_engine("fused")
+    out = api.ssfm(x, Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, gamma=0.0, amp=None, prgsBar=False))
+    assert rel_l2(out, fo.linear_fiber(x, 80, 0.2, 16, 193.1e12, 64e9)) < 1e-4
+    out = api.ssfm(x, Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, alpha=0.0, amp=None, prgsBar=False))
+    assert np.sum(np.abs(out) ** 2) == pytest.approx(np.sum(np.abs(x) ** 2), rel=2e-4)
+    api.eng.set_default_engine("auto")
