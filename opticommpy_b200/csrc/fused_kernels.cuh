@@ -1,14 +1,21 @@
 // Fused four-step FFT kernels of the split-step propagators (the sm_100a fast path, N = N1*N2,
 // N1 = 32*Q1, N2 = 32*Q2, Q in {8,16,32}).
 //
-// A length-N transform along a planar row x[n], n = N2*n1 + n2, is split as
-//     column pass : N1-point FFT over n1 for every column n2, times W_N^{n2 k1}   -> W[k1][n2]
-//     row pass    : N2-point FFT over n2 for every row k1                          -> X[k1 + N1 k2]
-// The inverse mirrors it.  Because the linear operator is diagonal in frequency and the Kerr
-// rotation is pointwise in time, one half step  ifft(fft(.)*L)  costs THREE passes over the data:
-//     k_col (… -> FFT_N1 -> twiddle)   k_row (FFT_N2 · L · IFFT_N2)   k_col (twiddle* -> IFFT_N1 -> …)
-// and every pointwise operation of the split-step loop (power, nonlinear phase, rotation,
-// convergence sums, max power) rides in the time-domain end of a column kernel.
+// A length-N transform of x[n], n = N2*n1 + n2, factors as
+//     time pass : N1-point FFT over n1 for every n2, times W_N^{n2 k1}      -> W[n2][k1]
+//     freq pass : N2-point FFT over n2 for every k1                          -> X[k1 + N1 k2]
+// and the inverse mirrors it.  The engine keeps every time-domain field TRANSPOSED in HBM
+// (index N1*n2 + n1), so that the time pass — the one that also carries every pointwise operation
+// of the split-step loop and therefore streams up to six arrays — works on contiguous rows with one
+// warp per row, while the strided pass (k_freq) only streams the W buffer:
+//     k_time : [.. -> IFFT_N1 ->] pointwise stage [-> FFT_N1 -> twiddle]      (contiguous rows)
+//     k_freq : FFT_N2 -> x linear operator -> IFFT_N2                         (column tiles, in place)
+// One half step ifft(fft(.)*L) therefore costs three passes over the data and the Kerr rotation,
+// power, convergence sums and max-power reduction ride inside k_time.
+//
+// W-row layout: position p = slot*Q1 + t holds k1 = (t*G1 + slot/Q1) + 32*brev<Q1>(slot % Q1);
+// it is whatever order the cooperative FFT leaves in registers, so loads and stores of W rows are
+// lane-contiguous.  k_freq and the operator table only need to agree on that order.
 //
 // Reference formulas restated here: optic/models/channels.py:388-390, 406-421, 424, 436, 493,
 // 517-519 (manakovSSF), :219-229 (ssfm), optic/dsp/equalization.py:1077, 1129 (DBP signs).
@@ -18,224 +25,236 @@
 
 namespace ocb {
 
-enum ColMode { COL_FWD = 0, COL_INV = 1, COL_FIRST = 2, COL_ITER = 3, COL_NLSE = 4 };
+enum TimeMode { TM_FWD = 0, TM_INV = 1, TM_FIRST = 2, TM_ITER = 3, TM_NLSE = 4 };
 
-struct ColArgs {
-    const float2* in;     // COL_FWD: time-domain field ; others: W-domain buffer
-    float2* out;          // COL_INV: time-domain field ; others: W-domain buffer
-    const float2* aux0;   // COL_FIRST: step-start field Ech ; COL_ITER: previous iterate E_conv
-    float2* aux1;         // COL_FIRST: E_hd (written)       ; COL_ITER: new iterate (written)
-    const float2* ehd;    // COL_ITER: E_hd (read)
-    float* pch;           // COL_FIRST: written ; COL_ITER: read
+struct TimeArgs {
+    const float2* in;     // TM_FWD: time-domain field ; others: W buffer
+    float2* out;          // TM_INV: time-domain field ; others: W buffer
+    const float2* aux0;   // TM_FIRST: step-start field Ech ; TM_ITER: previous iterate E_conv
+    float2* aux1;         // TM_FIRST: E_hd (written)       ; TM_ITER: new iterate (written)
+    const float2* ehd;    // TM_ITER: E_hd (read)
+    float* pch;           // TM_FIRST: written ; TM_ITER: read
     const float2* tw;     // [32][Q1]  exp(-2 pi i q ka / N1)
     const float2* tabV;   // [N2][32]  exp(-2 pi i n2 ka / N)
     const float2* tabU;   // [N2][Q1]  exp(-2 pi i n2 32 kq / N)
-    double* partials;     // COL_ITER reduction scratch
+    double* partials;     // TM_ITER reduction scratch
     double* sums;
     unsigned* ticket;
-    int64_t N;            // samples per row
-    int N2;               // columns
+    int64_t N;            // samples per polarisation row
+    int N2;               // number of time rows (n2)
     float cphi;           // dir*hz*(8/9)γ (FIRST) | dir*hz*(8/9)γ/2 (ITER) | γ hz (NLSE)
-    float out_scale;      // COL_INV: extra gain applied to the time-domain output
+    float out_scale;      // TM_INV: gain applied to the time-domain output
 };
 
 // phase rotation exp(j ph): short polynomial for the small per-step phases (|ph| < 0.5 rad,
-// truncation error < 1e-9), libm sincosf otherwise.
+// truncation error < 1e-9); the rare large phase takes an out-of-line libm call so that the 32
+// unrolled call sites stay small (instruction-cache footprint).
+__device__ __noinline__ float2 phase_rot_slow(float ph) {
+    float s, c;
+    sincosf(ph, &s, &c);
+    return make_float2(c, s);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float2 phase_rot(float ph) {
     float s, c;
-    if (fabsf(ph) < 0.5f) {
+    if (fabsf(ph) >= 0.5f) return phase_rot_slow(ph);
+    {
         const float x2 = ph * ph;
         s = ph * fmaf(x2, fmaf(x2, fmaf(x2, -1.9841270e-4f, 8.3333333e-3f), -1.6666667e-1f), 1.0f);
         c = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
-    } else {
-        sincosf(ph, &s, &c);
     }
     return make_float2(c, s);
 }
 
 // ------------------------------------------------------------------------------------------
-// Column kernel.  One CTA = one tile of C adjacent columns, both polarisations (NP = 2) or one
-// (NP = 1).  Thread (pol, q, c): time-domain rows Q1*a' + q (a' < 32), frequency rows
-// (q*G + g) + 32*kq.  A warp touches 32/C adjacent rows x C*8 contiguous bytes per access.
+// Time kernel.  64-thread CTA = 64/Q1 row tasks; a task is (time row n2, polarisation) and is owned
+// by Q1 threads (one warp when N1 = 1024).  With NP = 2 the x and y tasks of a row sit in the same
+// CTA and share |E|^2 through shared memory.  Every global access is lane-contiguous.
 // ------------------------------------------------------------------------------------------
-template <int Q1, int C, int NP, int MODE>
-__global__ void __launch_bounds__(NP* Q1* C, (NP * Q1 * C <= 256) ? 2 : 1)
-k_col(const ColArgs A) {
+template <int Q1, int NP, int MODE>
+__global__ void __launch_bounds__(64)
+k_time(const TimeArgs A) {
     using namespace fft;
-    constexpr int G = 32 / Q1, STR = Q1 * C + C, NT = NP * Q1 * C;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);              // [32*Q1]
-    float2* Vs = tw + 32 * Q1;                                      // [C][32]
-    float2* Us = Vs + C * 32;                                       // [C][Q1]
-    float* xbuf = reinterpret_cast<float*>(Us + C * Q1);            // [NP][2][32*STR]
+    constexpr int G = 32 / Q1, N1 = 32 * Q1, TASKS = 64 / Q1;
+    constexpr int STR = Q1 + 1, GBUF = 32 * STR + (Q1 < 32 ? Q1 : 0);
+    __shared__ float xbuf[TASKS * 2 * GBUF];
+    __shared__ float pbuf[(MODE == TM_FIRST || MODE == TM_ITER) ? TASKS * N1 : 1];
 
-    const int tid = threadIdx.x;
-    const int pol = tid / (Q1 * C);
-    const int q = (tid % (Q1 * C)) / C;
-    const int c = tid % C;
-    const int col0 = blockIdx.x * C;
-    const int N2 = A.N2;
-    const int64_t rowoff = (int64_t)pol * A.N + col0 + c;
-    float* xr = xbuf + (size_t)pol * 2 * 32 * STR;
-    float* xi = xr + 32 * STR;
-
-    for (int i = tid; i < 32 * Q1; i += NT) tw[i] = A.tw[i];
-    for (int i = tid; i < C * 32; i += NT) Vs[i] = A.tabV[(int64_t)(col0 + i / 32) * 32 + (i % 32)];
-    for (int i = tid; i < C * Q1; i += NT) Us[i] = A.tabU[(int64_t)(col0 + i / Q1) * Q1 + (i % Q1)];
-    __syncthreads();
-    auto bsync = [] { __syncthreads(); };
+    const int tid = threadIdx.x, grp = tid / Q1, t = tid % Q1;
+    const int task = blockIdx.x * TASKS + grp;
+    const int row = task / NP, pol = task % NP;
+    float* xr = xbuf + grp * 2 * GBUF;
+    float* xi = xr + GBUF;
+    const int64_t base = (int64_t)pol * A.N + (int64_t)row * N1;
+    auto wsync = [] { __syncwarp(); };
+    const float2* tw = A.tw;  // 8 KB table, L1-resident
 
     float2 v[32];
-
-    // ---- enter: either the time-domain field (FWD) or the W-domain buffer (inverse first) ----
-    if constexpr (MODE == COL_FWD) {
-        const float2* src = A.in + rowoff;
+    float2 wV[G];
 #pragma unroll
-        for (int a = 0; a < 32; ++a) v[a] = __ldg(src + (int64_t)(Q1 * a + q) * N2);
+    for (int g = 0; g < G; ++g) wV[g] = __ldg(A.tabV + (int64_t)row * 32 + t * G + g);
+    const float2* Urow = A.tabU + (int64_t)row * Q1;
+
+    // Secondary streams of the pointwise stage: start their HBM->L2 fetch now so that it overlaps the
+    // W-row load and the inverse transform (one 128-byte line per lane and trip).
+    if constexpr (MODE == TM_FIRST || MODE == TM_ITER) {
+        constexpr int LINES = N1 * 8 / 128;
+        for (int l = t; l < LINES; l += Q1) {
+            prefetch_l2(reinterpret_cast<const char*>(A.aux0 + base) + l * 128);
+            if constexpr (MODE == TM_ITER) prefetch_l2(reinterpret_cast<const char*>(A.ehd + base) + l * 128);
+        }
+        if constexpr (MODE == TM_ITER) {
+            if (pol == 0)
+                for (int l = t; l < LINES / 2; l += Q1)
+                    prefetch_l2(reinterpret_cast<const char*>(A.pch + (int64_t)row * N1) + l * 128);
+        }
+    }
+
+    // ---- enter ----------------------------------------------------------------------------------
+    if constexpr (MODE == TM_FWD) {
+        const float2* src = A.in + base;
+#pragma unroll
+        for (int a = 0; a < 32; ++a) v[a] = __ldg(src + Q1 * a + t);
     } else {
-        const float2* src = A.in + rowoff;
+        const float2* src = A.in + base;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) v[s] = __ldg(src + s * Q1 + t);
         static_for<0, G>([&](auto gg) {
             constexpr int GI = decltype(gg)::value;
             static_for<0, Q1>([&](auto kk) {
                 constexpr int KQ = decltype(kk)::value, SLOT = GI * Q1 + brev<Q1>(KQ);
-                v[SLOT] = __ldg(src + (int64_t)((q * G + GI) + 32 * KQ) * N2);
-            });
-        });
-        static_for<0, G>([&](auto gg) {
-            constexpr int GI = decltype(gg)::value;
-            const float2 wv = Vs[c * 32 + q * G + GI];
-            static_for<0, Q1>([&](auto kk) {
-                constexpr int KQ = decltype(kk)::value, SLOT = GI * Q1 + brev<Q1>(KQ);
-                const float2 w = cmul(wv, Us[c * Q1 + KQ]);
+                const float2 w = cmul(wV[GI], __ldg(Urow + KQ));
                 v[SLOT] = cmul_conj(v[SLOT], w);  // conj twiddle W_N^{-n2 k1}
             });
         });
-        coop_fft_inverse<Q1, C, C>(v, xr, xi, tw, q, c, bsync);  // v[a'] = field at row Q1*a' + q
+        coop_fft_inverse<Q1, 1, 1>(v, xr, xi, tw, t, 0, wsync);  // v[a'] = sample n1 = Q1*a' + t
+        __syncwarp();
     }
 
-    // ---- time-domain work -------------------------------------------------------------------
+    // ---- pointwise stage in the time domain ---------------------------------------------------------
     float s_num = 0.f, s_den = 0.f, s_max = 0.f;
-    if constexpr (MODE == COL_INV) {
-        float2* dst = A.out + rowoff;
+    if constexpr (MODE == TM_INV) {
+        float2* dst = A.out + base;
 #pragma unroll
-        for (int a = 0; a < 32; ++a)
-            dst[(int64_t)(Q1 * a + q) * N2] = make_float2(v[a].x * A.out_scale, v[a].y * A.out_scale);
+        for (int a = 0; a < 32; ++a) dst[Q1 * a + t] = make_float2(v[a].x * A.out_scale, v[a].y * A.out_scale);
         return;
     }
-    if constexpr (MODE == COL_NLSE) {  // channels.py:225
+    if constexpr (MODE == TM_NLSE) {  // channels.py:225
 #pragma unroll
         for (int a = 0; a < 32; ++a) v[a] = cmul(v[a], phase_rot(A.cphi * cabs2(v[a])));
-        __syncthreads();  // the forward transform below reuses the exchange buffers
     }
-    if constexpr (MODE == COL_FIRST || MODE == COL_ITER) {
+    if constexpr (MODE == TM_FIRST || MODE == TM_ITER) {
         static_assert(NP == 2, "Manakov modes need both polarisations in the CTA");
-        __syncthreads();  // exchange buffers are free again; reuse xr[pol] to share |E|² across pols
-        if constexpr (MODE == COL_FIRST) {
+        float* pown = pbuf + grp * N1;
+        const float* poth = pbuf + (grp ^ 1) * N1;  // the other polarisation of the same row
+        if constexpr (MODE == TM_FIRST) {
             // v = E_hd (store it); power of the step-start field Ech  (channels.py:388)
-            float2* ehd_out = A.aux1 + rowoff;
-            const float2* ech = A.aux0 + rowoff;
+            float2* ehd_out = A.aux1 + base;
+            const float2* ech = A.aux0 + base;
 #pragma unroll
             for (int a = 0; a < 32; ++a) {
-                const int64_t o = (int64_t)(Q1 * a + q) * N2;
-                ehd_out[o] = v[a];
-                xr[a * STR + q * C + c] = cabs2(__ldg(ech + o));
+                ehd_out[Q1 * a + t] = v[a];
+                pown[Q1 * a + t] = cabs2(__ldg(ech + Q1 * a + t));
             }
         } else {
             // v = E_fd: convergence sums against the previous iterate, store as the new iterate
-            const float2* ec = A.aux0 + rowoff;
-            float2* ec_new = A.aux1 + rowoff;
+            const float2* ec = A.aux0 + base;
+            float2* ec_new = A.aux1 + base;
 #pragma unroll
             for (int a = 0; a < 32; ++a) {
-                const int64_t o = (int64_t)(Q1 * a + q) * N2;
-                const float2 e = __ldg(ec + o);
+                const float2 e = __ldg(ec + Q1 * a + t);
                 s_num += cabs2(make_float2(v[a].x - e.x, v[a].y - e.y));  // channels.py:517
                 s_den += cabs2(e);
-                ec_new[o] = v[a];
-                xr[a * STR + q * C + c] = cabs2(v[a]);
+                ec_new[Q1 * a + t] = v[a];
+                pown[Q1 * a + t] = cabs2(v[a]);
             }
         }
         __syncthreads();
-        const float* other = xbuf + (size_t)(1 - pol) * 2 * 32 * STR;
-        float* pch = A.pch + col0 + c;
-        const float2* ehd = (MODE == COL_ITER) ? A.ehd + rowoff : nullptr;
+        float* pch = A.pch + (int64_t)row * N1;
+        const float2* ehd = (MODE == TM_ITER) ? A.ehd + base : nullptr;
 #pragma unroll
         for (int a = 0; a < 32; ++a) {
-            const int64_t o = (int64_t)(Q1 * a + q) * N2;
-            const float P = xr[a * STR + q * C + c] + other[a * STR + q * C + c];
+            const float P = pown[Q1 * a + t] + poth[Q1 * a + t];
             float ph;
-            if constexpr (MODE == COL_FIRST) {
-                if (pol == 0) pch[o] = P;
+            if constexpr (MODE == TM_FIRST) {
+                if (pol == 0) pch[Q1 * a + t] = P;
                 ph = A.cphi * P;  // φ = (8/9)γ(P+P)/2, channels.py:390/493 with E_conv == Ech
             } else {
                 s_max = fmaxf(s_max, P);
-                ph = A.cphi * (__ldg(pch + o) + P);  // channels.py:436
-                v[a] = __ldg(ehd + o);
+                ph = A.cphi * (__ldg(pch + Q1 * a + t) + P);  // channels.py:436
+                v[a] = __ldg(ehd + Q1 * a + t);
             }
             v[a] = cmul(v[a], phase_rot(ph));  // channels.py:414-417
         }
-        __syncthreads();  // before the forward transform reuses the exchange buffers
     }
 
-    // ---- leave: forward column FFT + inter-pass twiddle -> W-domain buffer ----------------------
-    coop_fft_forward<Q1, C, C>(v, xr, xi, tw, q, c, bsync);
+    // ---- leave: forward FFT over n1 + inter-pass twiddle -> W row ---------------------------------------
+    coop_fft_forward<Q1, 1, 1>(v, xr, xi, tw, t, 0, wsync);
     {
-        float2* dst = A.out + rowoff;
+        float2* dst = A.out + base;
         static_for<0, G>([&](auto gg) {
             constexpr int GI = decltype(gg)::value;
-            const float2 wv = Vs[c * 32 + q * G + GI];
             static_for<0, Q1>([&](auto kk) {
                 constexpr int KQ = decltype(kk)::value, SLOT = GI * Q1 + brev<Q1>(KQ);
-                const float2 w = cmul(wv, Us[c * Q1 + KQ]);
-                dst[(int64_t)((q * G + GI) + 32 * KQ) * N2] = cmul(v[SLOT], w);
+                const float2 w = cmul(wV[GI], __ldg(Urow + KQ));
+                dst[SLOT * Q1 + t] = cmul(v[SLOT], w);
             });
         });
     }
-    if constexpr (MODE == COL_ITER) {
-        if (pol == 1) s_max = 0.f;  // both pol threads saw the same total power
+    if constexpr (MODE == TM_ITER) {
+        if (pol == 1) s_max = 0.f;  // both polarisation tasks saw the same total power
         block_reduce3_finalize(s_num, s_den, s_max, A.partials, A.sums, A.ticket);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Row kernel: for every row k1 of the W-domain buffer:  FFT_N2 -> x LP[k1][.] -> IFFT_N2, in place.
-// Q2 threads own one row; a 256-thread CTA processes 256/Q2 rows per trip (grid-stride).
-// LP is the linear operator in the kernel's own consumption order:
-//   LP[k1*N2 + s*Q2 + t] = scale * exp((a + j b ω_k²) h),  k = k1 + N1*(ka + 32 kq),
-//   ka = t*G + s/Q2, kq = brev<Q2>(s % Q2)
+// Frequency kernel: for a tile of C adjacent W positions p (all N2 rows of one polarisation):
+// FFT_N2 over n2 -> x LP -> IFFT_N2, in place.  Thread (q, c) owns rows n2 = Q2*a + q of column
+// p0 + c; a warp touches 32/C rows x C*8 contiguous bytes per access.
+// LP is stored in consumption order: LP[((tile*32 + slot)*Q2 + q)*C + c], see k_tab_linop_perm.
 // ------------------------------------------------------------------------------------------
-template <int Q2>
-__global__ void __launch_bounds__(256)
-k_row(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __restrict__ tw_g, int N1,
-      int64_t n_rows) {
+template <int Q2, int C>
+__global__ void __launch_bounds__(Q2* C, (Q2 * C <= 256) ? 2 : 1)
+k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __restrict__ tw, int N1) {
     using namespace fft;
-    constexpr int S2 = 32 * Q2, STR = Q2 + 1, RPB = 256 / Q2;
-    constexpr int GBUF = 32 * STR + (Q2 < 32 ? Q2 : 0);  // stagger groups sharing a warp
+    constexpr int STR = Q2 * C + C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);   // [32*Q2]
-    float* xbuf = reinterpret_cast<float*>(tw + 32 * Q2);
-    const int tid = threadIdx.x, grp = tid / Q2, q = tid % Q2;
-    float* xr = xbuf + (size_t)grp * 2 * GBUF;
-    float* xi = xr + GBUF;
-    for (int i = tid; i < 32 * Q2; i += 256) tw[i] = tw_g[i];
-    __syncthreads();
-    auto wsync = [] { __syncwarp(); };
+    float* xr = reinterpret_cast<float*>(smem_raw);  // [32*STR]
+    float* xi = xr + 32 * STR;
+    const int tid = threadIdx.x, q = tid / C, c = tid % C;
+    const int tiles_per_pol = N1 / C;
+    const int pol = blockIdx.x / tiles_per_pol, tile = blockIdx.x % tiles_per_pol;
+    float2* base = W + ((int64_t)pol * (32 * Q2)) * N1 + tile * C + c;  // row n2 = 0 of this column
+    const float2* lp = LP + (int64_t)tile * 32 * (Q2 * C) + q * C + c;
+    auto bsync = [] { __syncthreads(); };
 
-    for (int64_t row0 = (int64_t)blockIdx.x * RPB; row0 < n_rows; row0 += (int64_t)gridDim.x * RPB) {
-        const int64_t row = row0 + grp;
-        if (row >= n_rows) continue;  // n_rows is a multiple of RPB in practice (whole warps stay together)
-        float2* p = W + row * S2;
-        const float2* lp = LP + (row % N1) * S2 + q;
-        float2 v[32];
+    float2 v[32];
 #pragma unroll
-        for (int a = 0; a < 32; ++a) v[a] = p[Q2 * a + q];
-        coop_fft_forward<Q2, 1, 1>(v, xr, xi, tw, q, 0, wsync);
+    for (int a = 0; a < 32; ++a) v[a] = base[(int64_t)(Q2 * a + q) * N1];
+    coop_fft_forward<Q2, C, C>(v, xr, xi, tw, q, c, bsync);
 #pragma unroll
-        for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], __ldg(lp + s * Q2));
-        __syncwarp();
-        coop_fft_inverse<Q2, 1, 1>(v, xr, xi, tw, q, 0, wsync);
+    for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], __ldg(lp + s * (Q2 * C)));
+    __syncthreads();
+    coop_fft_inverse<Q2, C, C>(v, xr, xi, tw, q, c, bsync);
 #pragma unroll
-        for (int a = 0; a < 32; ++a) p[Q2 * a + q] = v[a];
-        __syncwarp();
+    for (int a = 0; a < 32; ++a) base[(int64_t)(Q2 * a + q) * N1] = v[a];
+}
+
+// ------------------------------------------------------------------------------------------
+// Layout conversion: planar natural order [r][N2*n1 + n2]  <->  engine order [r][N1*n2 + n1]
+// (a tiled matrix transpose per row r).  in: (rows_in x cols_in) -> out: (cols_in x rows_in).
+// ------------------------------------------------------------------------------------------
+__global__ void k_transpose(const float2* __restrict__ in, float2* __restrict__ out, int rows_in, int cols_in,
+                            float scale) {
+    __shared__ float2 tile[32][33];
+    const int64_t plane = (int64_t)rows_in * cols_in * blockIdx.z;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        tile[j][threadIdx.x] = in[plane + (int64_t)(r0 + j) * cols_in + c0 + threadIdx.x];
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        float2 e = tile[threadIdx.x][j];
+        out[plane + (int64_t)(c0 + j) * rows_in + r0 + threadIdx.x] = make_float2(e.x * scale, e.y * scale);
     }
 }
 
@@ -267,21 +286,31 @@ __global__ void k_tab_inter(float2* V, float2* U, int N2, int Q1, int64_t N) {
         U[i] = make_float2((float)c, (float)s);
     }
 }
-// Linear operator in the row kernel's consumption order (see k_row).  a, b, Fs, h, scale as in
-// k_linop_table: value = scale * exp((a + j b ω_k²) h), ω_k = 2π Fs fftfreq(N)[k].
-template <int Q2>
-__global__ void k_tab_linop_perm(float2* __restrict__ LP, int N1, int64_t N, double a, double b, double Fs,
-                                 double h, double scale) {
-    using namespace fft;
-    constexpr int S2 = 32 * Q2, G = 32 / Q2;
+__host__ __device__ inline int brev_rt(int v, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) r |= ((v >> b) & 1) << (bits - 1 - b);
+    return r;
+}
+// Linear operator in k_freq's consumption order.  Entry i = ((tile*32 + slot2)*Q2 + t2)*C + c is the
+// operator at frequency k = k1(p) + N1*k2 with p = tile*C + c,
+//   k1(p) = ((p % Q1)*G1 + (p / Q1) / Q1) + 32*brev<Q1>((p / Q1) % Q1)      (W-row layout, see header)
+//   k2    = (t2*G2 + slot2 / Q2) + 32*brev<Q2>(slot2 % Q2)
+// value = scale * exp((a + j b ω_k²) h), ω_k = 2π Fs fftfreq(N)[k]   (channels.py:368, 406)
+__global__ void k_tab_linop_perm(float2* __restrict__ LP, int Q1, int Q2, int C, int64_t N, double a, double b,
+                                 double Fs, double h, double scale) {
     const double two_pi = 6.283185307179586476925286766559;
+    const int N1 = 32 * Q1, G1 = 32 / Q1, G2 = 32 / Q2;
+    const int lq1 = fft::ilog2(Q1), lq2 = fft::ilog2(Q2);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k1 = i / S2;
-        const int r = (int)(i % S2), s = r / Q2, t = r % Q2;
-        const int ka = t * G + s / Q2;
-        int kq = 0, pp = s % Q2;
-        for (int bit = 0; bit < ilog2(Q2); ++bit) kq |= ((pp >> bit) & 1) << (ilog2(Q2) - 1 - bit);
-        const int64_t k = k1 + (int64_t)N1 * (ka + 32 * kq);
+        const int c = (int)(i % C);
+        const int t2 = (int)((i / C) % Q2);
+        const int slot2 = (int)((i / ((int64_t)C * Q2)) % 32);
+        const int64_t tile = i / ((int64_t)C * Q2 * 32);
+        const int p = (int)(tile * C + c);
+        const int s1 = p / Q1, t1 = p % Q1;
+        const int k1 = (t1 * G1 + s1 / Q1) + 32 * brev_rt(s1 % Q1, lq1);
+        const int k2 = (t2 * G2 + slot2 / Q2) + 32 * brev_rt(slot2 % Q2, lq2);
+        const int64_t k = k1 + (int64_t)N1 * k2;
         const int64_t kk = (k <= (N - 1) / 2) ? k : k - N;
         const double w = two_pi * Fs * ((double)kk / (double)N);
         const double amp = scale * exp(a * h);

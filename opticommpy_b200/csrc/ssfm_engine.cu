@@ -58,6 +58,7 @@ struct ocb_ssfm_plan {
     bool fused_ok = false, fused_tables_ready = false;
     int q1 = 0, q2 = 0;
     float2 *tw1 = nullptr, *tw2 = nullptr, *tabV = nullptr, *tabU = nullptr;
+    float2 *Cb = nullptr, *Nb = nullptr;  // third rotating field buffer, engine-layout noise copy
     // table cache keys
     double t1_h = NAN, t1_a = NAN, t1_b = NAN, t1_scale = NAN;
     // optional in-situ kernel timing (CUDA events on the launching stream); kinds:
@@ -96,7 +97,8 @@ static bool fused_geometry(int64_t N, int* q1, int* q2) {
 static int64_t fused_table_bytes(const ocb_ssfm_plan* p) {
     if (!p->fused_ok) return 0;
     return align_up(32ll * p->q1 * 8, 256) + align_up(32ll * p->q2 * 8, 256) +
-           align_up(32ll * p->q2 * 32 * 8, 256) + align_up(32ll * p->q2 * p->q1 * 8, 256);
+           align_up(32ll * p->q2 * 32 * 8, 256) + align_up(32ll * p->q2 * p->q1 * 8, 256) +
+           align_up((int64_t)p->rows * p->N * 8, 256) + align_up(p->N * 8, 256);
 }
 static int fused_manakov_run(ocb_ssfm_plan*, void*, const ocb_manakov_params*, const void*, const int32_t*, void*,
                              ocb_manakov_stats*, cudaStream_t);
@@ -170,6 +172,8 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
         p->tw2 = (float2*)c; c += align_up(32ll * p->q2 * 8, 256);
         p->tabV = (float2*)c; c += align_up(32ll * p->q2 * 32 * 8, 256);
         p->tabU = (float2*)c; c += align_up(32ll * p->q2 * p->q1 * 8, 256);
+        p->Cb = (float2*)c; c += align_up((int64_t)p->rows * p->N * 8, 256);
+        p->Nb = (float2*)c; c += align_up(p->N * 8, 256);
         p->fused_tables_ready = false;
     }
     OCB_CUDA(cudaMemset(p->sums, 0, 256));
