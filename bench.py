@@ -220,7 +220,6 @@ def main():
         stats = one_step()
     barrier()
     plan = _engine.get_plan(N_SAMPLES, 2)
-    _cabi.check(lib.ocb_ssfm_plan_profile(plan.handle, 1), "profile on")
 
     # ---- timed region: device-resident
     _cabi.launch_count_reset()
@@ -238,9 +237,16 @@ def main():
             tot_steps += stats["steps"]
             tot_iters += stats["iterations"]
     launches = _cabi.launch_count()
+    # ---- in-situ kernel timing: one more span of the same propagation with CUDA events recorded around
+    # every launch of the step loop (2048 samples per kernel kind); kept out of `value` because the
+    # event pairs serialise the otherwise speculative launch stream
     prof = (C.c_double * 6)()
-    _cabi.check(lib.ocb_ssfm_plan_profile_read(plan.handle, prof), "profile read")
-    _cabi.check(lib.ocb_ssfm_plan_profile(plan.handle, 0), "profile off")
+    if rank == 0:
+        _cabi.check(lib.ocb_ssfm_plan_profile(plan.handle, 1), "profile on")
+        rows.copy_(rows0)
+        manakov_rows_device(rows, channel_param(1), +1)
+        _cabi.check(lib.ocb_ssfm_plan_profile_read(plan.handle, prof), "profile read")
+        _cabi.check(lib.ocb_ssfm_plan_profile(plan.handle, 0), "profile off")
     t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -269,7 +275,9 @@ def main():
         peak, peak_src = measured_hbm_peak()
         mean_I = tot_iters / max(1, tot_steps)
         nl_ms, nl_n = prof[0], prof[1]
-        bytes_nl = 68.0 * N_SAMPLES  # Efd 16 + Ec 16 + Ehd 16 + Pch 4 read, rotated field 16 written
+        # fused engine: W row 16 + Ec 16 + Ehd 16 + Pch 4 read, new iterate 16 + W row 16 written = 84 B
+        # cuFFT engine NL pass: Efd 16 + Ec 16 + Ehd 16 + Pch 4 read, rotated field 16 written = 68 B
+        bytes_nl = (84.0 if plan.engine == "fused" else 68.0) * N_SAMPLES
         ach = bytes_nl / (nl_ms / max(nl_n, 1) * 1e-3) / 1e9 if nl_n else None
         step_bytes = (64.0 + 84.0 * mean_I) * N_SAMPLES  # SURVEY §8d model per SSFM step
         step_ach = step_bytes * tot_steps / (tot_ms * 1e-3) / 1e9
@@ -285,7 +293,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(host_np.nbytes + noise_bytes),
                     "d2h_bytes_per_step": int(out.nbytes)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_manakov_nl<false,2> (fused NL pass: convergence sums + phase + rotation)",
+            "engine": plan.engine,
+            "roofline": {"bound": "hbm", "kernel": ("k_time<32,2,TM_ITER> (IFFT_N1 + convergence sums + Kerr phase/rotation + FFT_N1)"
+                                                    if plan.engine == "fused" else
+                                                    "k_manakov_nl<false,2> (convergence sums + Kerr phase/rotation)"),
                          "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": None,
                          "launches_timed": int(nl_n), "avg_us": 1e3 * nl_ms / max(nl_n, 1),

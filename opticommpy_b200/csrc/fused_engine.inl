@@ -21,7 +21,8 @@ int launch_time(int Q1, const TimeArgs& a, cudaStream_t st) {
     return fail("fused engine: unsupported N1", __FILE__, __LINE__);
 }
 template <int Q2>
-int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st) {
+int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP, const long long* flag,
+                  long long step_id, cudaStream_t st) {
     static bool configured = false;
     constexpr int C = kFreqC;
     const size_t smem = (size_t)2 * 32 * (Q2 * C + C) * sizeof(float);
@@ -29,14 +30,15 @@ int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP,
         OCB_CUDA(cudaFuncSetAttribute(k_freq<Q2, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    OCB_LAUNCH((k_freq<Q2, C>), NP * N1 / C, Q2 * C, smem, st, W, LP, tw, N1);
+    OCB_LAUNCH((k_freq<Q2, C>), NP * N1 / C, Q2 * C, smem, st, W, LP, tw, N1, flag, step_id);
     return 0;
 }
-int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st) {
+int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st,
+                const long long* flag = nullptr, long long step_id = 0) {
     switch (Q2) {
-        case 8: return launch_freq_t<8>(W, LP, tw, N1, NP, st);
-        case 16: return launch_freq_t<16>(W, LP, tw, N1, NP, st);
-        case 32: return launch_freq_t<32>(W, LP, tw, N1, NP, st);
+        case 8: return launch_freq_t<8>(W, LP, tw, N1, NP, flag, step_id, st);
+        case 16: return launch_freq_t<16>(W, LP, tw, N1, NP, flag, step_id, st);
+        case 32: return launch_freq_t<32>(W, LP, tw, N1, NP, flag, step_id, st);
     }
     return fail("fused engine: unsupported N2", __FILE__, __LINE__);
 }
@@ -142,27 +144,48 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 if (launch_time<2, TM_FIRST>(p->q1, c1, st)) return 1;
             }
             int ec = cur, dst = (cur + 1) % 3;
-            for (int it = 0; it < q->maxIter; ++it) {  // channels.py:413
+            // Fixed-point loop (channels.py:413).  Iteration it+1 is enqueued BEFORE the outcome of
+            // iteration it is known; the finalising block of it sets a device flag when lim < tol and
+            // the speculative launches of the same step exit at once.  The host only reads a mailbox
+            // in mapped pinned memory, so the GPU never waits for a stream synchronisation.
+            const long long step_id = ++p->step_counter;
+            const bool speculate = !p->prof_on;
+            auto enqueue_iter = [&](int e_c, int d_st, unsigned long long seq) -> int {
                 {
                     ProfScope ps(p, 2, st);
-                    if (launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st)) return 1;  // :420-421 (frequency part)
+                    if (launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, p->conv_flag, step_id)) return 1;  // :420-421
                 }
-                {
-                    ProfScope ps(p, 0, st);
-                    TimeArgs ci = time_base(p);
-                    ci.in = Wb; ci.out = Wb; ci.aux0 = bufs[ec]; ci.aux1 = bufs[dst]; ci.ehd = p->Ehd; ci.pch = p->Pch;
-                    ci.cphi = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma * 0.5);
-                    if (launch_time<2, TM_ITER>(p->q1, ci, st)) return 1;  // :424, :436, :414-417
+                ProfScope ps(p, 0, st);
+                TimeArgs ci = time_base(p);
+                ci.in = Wb; ci.out = Wb; ci.aux0 = bufs[e_c]; ci.aux1 = bufs[d_st]; ci.ehd = p->Ehd; ci.pch = p->Pch;
+                ci.cphi = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma * 0.5);
+                ci.ext.mail = p->d_mail; ci.ext.converged_step = p->conv_flag; ci.ext.step_id = step_id;
+                ci.ext.seq = seq; ci.ext.tol = q->tol;
+                return launch_time<2, TM_ITER>(p->q1, ci, st);  // :424, :436, :414-417
+            };
+            unsigned long long seq_cur = ++p->mail_seq;
+            if (enqueue_iter(ec, dst, seq_cur)) return 1;
+            for (int it = 0; it < q->maxIter; ++it) {
+                unsigned long long seq_next = 0;
+                const int third = 3 - ec - dst;
+                if (speculate && it + 1 < q->maxIter) {
+                    seq_next = ++p->mail_seq;
+                    if (enqueue_iter(dst, third, seq_next)) return 1;
                 }
-                if (fetch_sums(p, st)) return 1;
+                if (wait_mail(p, seq_cur, st)) return 1;
                 const double lim = sqrt(p->h_sums[0]) / sqrt(p->h_sums[1]);  // channels.py:517-519
+                const bool converged = p->h_sums[3] != 0.0;  // the device's decision (same formula, same doubles)
                 S.iterations++;
                 S.last_lim = lim;
-                const int third = 3 - ec - dst;
                 ec = dst;  // Ex_conv = Ech_x_fd (channels.py:426-427)
                 dst = third;
-                if (lim < q->tol) break;                     // channels.py:429
-                if (it == q->maxIter - 1) S.nonconverged++;  // channels.py:431-434
+                if (converged) break;                        // channels.py:429
+                if (it == q->maxIter - 1) { S.nonconverged++; break; }  // channels.py:431-434
+                if (!speculate) {
+                    seq_next = ++p->mail_seq;
+                    if (enqueue_iter(ec, dst, seq_next)) return 1;
+                }
+                seq_cur = seq_next;
             }
             cur = ec;
             maxP = p->h_sums[2];

@@ -44,6 +44,7 @@ struct TimeArgs {
     int N2;               // number of time rows (n2)
     float cphi;           // dir*hz*(8/9)γ (FIRST) | dir*hz*(8/9)γ/2 (ITER) | γ hz (NLSE)
     float out_scale;      // TM_INV: gain applied to the time-domain output
+    FinalizeExt ext;      // TM_ITER: host mailbox + convergence flag (ext.mail == nullptr: unused)
 };
 
 // phase rotation exp(j ph): short polynomial for the small per-step phases (|ph| < 0.5 rad,
@@ -77,6 +78,10 @@ k_time(const TimeArgs A) {
     using namespace fft;
     constexpr int G = 32 / Q1, N1 = 32 * Q1, TASKS = 64 / Q1;
     constexpr int STR = Q1 + 1, GBUF = 32 * STR + (Q1 < 32 ? Q1 : 0);
+    if constexpr (MODE == TM_ITER) {
+        // speculative launch of an iteration whose predecessor already converged: nothing to do
+        if (A.ext.mail && *reinterpret_cast<volatile long long*>(A.ext.converged_step) == A.ext.step_id) return;
+    }
     __shared__ float xbuf[TASKS * 2 * GBUF];
     __shared__ float pbuf[(MODE == TM_FIRST || MODE == TM_ITER) ? TASKS * N1 : 1];
 
@@ -203,7 +208,7 @@ k_time(const TimeArgs A) {
     }
     if constexpr (MODE == TM_ITER) {
         if (pol == 1) s_max = 0.f;  // both polarisation tasks saw the same total power
-        block_reduce3_finalize(s_num, s_den, s_max, A.partials, A.sums, A.ticket);
+        block_reduce3_finalize(s_num, s_den, s_max, A.partials, A.sums, A.ticket, &A.ext);
     }
 }
 
@@ -215,8 +220,10 @@ k_time(const TimeArgs A) {
 // ------------------------------------------------------------------------------------------
 template <int Q2, int C>
 __global__ void __launch_bounds__(Q2* C, (Q2 * C <= 256) ? 2 : 1)
-k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __restrict__ tw, int N1) {
+k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __restrict__ tw, int N1,
+       const long long* __restrict__ converged_step, long long step_id) {
     using namespace fft;
+    if (converged_step && *reinterpret_cast<const volatile long long*>(converged_step) == step_id) return;
     constexpr int STR = Q2 * C + C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xr = reinterpret_cast<float*>(smem_raw);  // [32*STR]

@@ -49,6 +49,12 @@ struct ocb_ssfm_plan {
     void* fft_area = nullptr;
     // pinned host mailbox for the convergence scalars
     double* h_sums = nullptr;
+    // zero-copy mailbox (mapped pinned memory) + device flag for the sync-free fixed-point loop
+    Mail* h_mail = nullptr;   // host view
+    Mail* d_mail = nullptr;   // device view of the same memory
+    long long* conv_flag = nullptr;  // device: id of the last step whose loop converged
+    unsigned long long mail_seq = 0;
+    long long step_counter = 0;
     // staging for the _host variants
     void* stage_dev = nullptr;
     int64_t stage_bytes = 0;
@@ -131,6 +137,11 @@ extern "C" int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out) {
     }
     cudaError_t e = cudaHostAlloc((void**)&p->h_sums, 8 * sizeof(double), cudaHostAllocDefault);
     if (e != cudaSuccess) { ocb_ssfm_plan_destroy(p); return fail("cudaHostAlloc failed", __FILE__, __LINE__); }
+    e = cudaHostAlloc((void**)&p->h_mail, kMailSlots * sizeof(Mail), cudaHostAllocMapped);
+    if (e != cudaSuccess) { ocb_ssfm_plan_destroy(p); return fail("cudaHostAlloc(mapped) failed", __FILE__, __LINE__); }
+    memset(p->h_mail, 0, kMailSlots * sizeof(Mail));
+    e = cudaHostGetDevicePointer((void**)&p->d_mail, p->h_mail, 0);
+    if (e != cudaSuccess) { ocb_ssfm_plan_destroy(p); return fail("cudaHostGetDevicePointer failed", __FILE__, __LINE__); }
     *out = p;
     return 0;
 }
@@ -164,7 +175,7 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
     p->T2 = (float2*)c; c += align_up(p->N * (int64_t)sizeof(float2), 256);
     p->Pch = (float*)c; c += align_up(((int64_t)(p->rows + 1) / 2) * p->N * sizeof(float), 256);
     p->partials = (double*)c; c += align_up((int64_t)p->max_blocks * 3 * sizeof(double), 256);
-    p->sums = (double*)c; p->ticket = (unsigned*)(c + 64); c += 256;
+    p->sums = (double*)c; p->ticket = (unsigned*)(c + 64); p->conv_flag = (long long*)(c + 128); c += 256;
     p->fft_area = c; c += align_up((int64_t)p->fft_work, 256);
     if (p->fft_work > 0) OCB_CUFFT(cufftSetWorkArea(p->fft, p->fft_area));
     if (p->fused_ok) {
@@ -231,6 +242,7 @@ extern "C" int ocb_ssfm_plan_destroy(ocb_ssfm_plan* p) {
         for (auto& e : p->prof_ev[k]) cudaEventDestroy(e);
     if (p->fft_ok) cufftDestroy(p->fft);
     if (p->h_sums) cudaFreeHost(p->h_sums);
+    if (p->h_mail) cudaFreeHost(p->h_mail);
     if (p->stage_dev) cudaFree(p->stage_dev);
     delete p;
     return 0;
@@ -302,6 +314,24 @@ static int launch_power_stats(ocb_ssfm_plan* p, const float2* E, int64_t N, int 
     else OCB_LAUNCH(k_power_stats<1>, g, 256, 0, st, E, N, K, p->partials, p->sums, p->ticket);
     return 0;
 }
+// Wait until the finalising block of the launch tagged `seq` has published its mail (spin on mapped
+// pinned memory; the stream is polled now and then so that a device fault cannot hang the host).
+static int wait_mail(ocb_ssfm_plan* p, unsigned long long seq, cudaStream_t st) {
+    volatile Mail* mb = p->h_mail + (seq % kMailSlots);
+    unsigned spins = 0;
+    while (mb->seq != seq) {
+        if ((++spins & 0xFFFF) == 0) {
+            cudaError_t e = cudaStreamQuery(st);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return fail(cudaGetErrorString(e), __FILE__, __LINE__);
+            if (e == cudaSuccess && mb->seq != seq) return fail("wait_mail: stream drained without the expected mail", __FILE__, __LINE__);
+        }
+    }
+    __sync_synchronize();
+    p->h_sums[0] = mb->sums[0]; p->h_sums[1] = mb->sums[1]; p->h_sums[2] = mb->sums[2];
+    p->h_sums[3] = (double)mb->converged;
+    return 0;
+}
+
 static int fetch_sums(ocb_ssfm_plan* p, cudaStream_t st) {
     OCB_CUDA(cudaMemcpyAsync(p->h_sums, p->sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     OCB_CUDA(cudaStreamSynchronize(st));

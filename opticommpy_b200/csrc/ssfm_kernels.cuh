@@ -53,10 +53,30 @@ __global__ void k_mul_table(float2* __restrict__ F, const float2* __restrict__ T
 // Block-level reduction of (sum, sum, max) with a deterministic "last block finalises" tail.
 // partials: [gridDim.x][3] doubles ; out: 3 doubles ; ticket: 1 uint (self-resetting).
 // ------------------------------------------------------------------------------------------
+// Host mailbox (mapped pinned memory) + device-side convergence flag used by the step loop to avoid
+// a stream synchronisation per fixed-point iteration: the finalising block publishes the sums and
+// the decision `lim < tol` (channels.py:429), speculatively enqueued launches of the same step read
+// the flag and exit.
+struct Mail {
+    double sums[3];
+    unsigned long long seq;  // written last, after a system-scope fence
+    int converged;
+    int pad;
+};
+constexpr int kMailSlots = 8;  // ring: the device runs at most one speculative iteration ahead of the host
+struct FinalizeExt {
+    Mail* mail;                 // ring of kMailSlots entries, slot = seq % kMailSlots (nullptr: plain reduction)
+    long long* converged_step;  // device flag
+    long long step_id;
+    unsigned long long seq;
+    double tol;
+};
+
 __device__ __forceinline__ void block_reduce3_finalize(float s0, float s1, float m,
                                                        double* __restrict__ partials,
                                                        double* __restrict__ out,
-                                                       unsigned* __restrict__ ticket) {
+                                                       unsigned* __restrict__ ticket,
+                                                       const FinalizeExt* ext = nullptr) {
     __shared__ double sh0[32], sh1[32], sh2[32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -100,6 +120,15 @@ __device__ __forceinline__ void block_reduce3_finalize(float s0, float s1, float
         for (int w = 0; w < nw; ++w) { ta += sh0[w]; tb += sh1[w]; tc = fmax(tc, sh2[w]); }
         out[0] = ta; out[1] = tb; out[2] = tc;
         *ticket = 0u;  // ready for the next launch
+        if (ext && ext->mail) {
+            const int conv = (sqrt(ta) / sqrt(tb) < ext->tol) ? 1 : 0;  // channels.py:517-519, 429
+            if (conv) *ext->converged_step = ext->step_id;
+            volatile Mail* mb = ext->mail + (ext->seq % kMailSlots);
+            mb->sums[0] = ta; mb->sums[1] = tb; mb->sums[2] = tc;
+            mb->converged = conv;
+            __threadfence_system();
+            mb->seq = ext->seq;
+        }
     }
 }
 
