@@ -1,0 +1,95 @@
+"""Multi-GPU sharding of independent propagation / DSP units.
+
+The hot path has no data-path collective: WDM channels for back-propagation, Monte-Carlo noise
+seeds and power-sweep points are independent waveforms.  Units are block-partitioned over the
+ranks of one ``torch.distributed`` job (one process per GPU, NCCL over NVLink on the GPU box, gloo
+in the CPU tests), every rank runs its units with the single-GPU functions of this package, and
+ONE collective at the end returns the results to every rank (``all_gather``) — the only
+communication of the path.
+
+    units = [...]                                  # identical list on every rank
+    mine  = shard_units(len(units))                # indices this rank owns
+    local = {i: manakovSSF(units[i], param.copy()) for i in mine}
+    full  = gather_results(local, len(units))      # list of numpy arrays, same on every rank
+
+Note on semantics: the reference's K-column batching couples the columns of one call through
+``max(phiRot)`` and the Frobenius norm (channels.py:394, 517), so independent waveforms are
+separate calls here (K = 1 each), which reproduces the per-waveform reference results.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def world():
+    d = _dist()
+    return (d.get_rank(), d.get_world_size()) if d else (0, 1)
+
+
+def shard_units(n_units: int, rank: int | None = None, world_size: int | None = None):
+    """Contiguous block partition of ``range(n_units)``; the first ``n_units % world`` ranks get one
+    extra unit (11 channels over 8 GPUs -> 2,2,2,1,1,1,1,1)."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, extra = divmod(n_units, world_size)
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
+
+
+def owner_of(unit: int, n_units: int, world_size: int) -> int:
+    base, extra = divmod(n_units, world_size)
+    edge = extra * (base + 1)
+    return unit // (base + 1) if unit < edge else extra + (unit - edge) // max(base, 1)
+
+
+def gather_results(local: dict, n_units: int, device=None):
+    """All-gather per-unit numpy results.  ``local`` maps unit index -> ndarray; every unit must have
+    the same shape and dtype.  Ragged ownership (n_units not divisible by the world size) is padded
+    to the largest shard so that a single equal-size ``all_gather`` suffices."""
+    import torch
+
+    d = _dist()
+    rank, ws = world()
+    if d is None or ws == 1:
+        return [np.asarray(local[i]) for i in range(n_units)]
+    mine = shard_units(n_units, rank, ws)
+    assert sorted(local) == mine, "local results do not match this rank's shard"
+    per_rank = -(-n_units // ws)
+    sample = np.asarray(local[mine[0]]) if mine else None
+    # ranks with an empty shard learn shape/dtype from rank 0 (which always owns unit 0)
+    meta = [sample.shape, str(sample.dtype)] if rank == 0 else None
+    box = [meta]
+    d.broadcast_object_list(box, src=0)
+    shape, dtype = tuple(box[0][0]), np.dtype(box[0][1])
+    backend = d.get_backend()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    is_complex = np.issubdtype(dtype, np.complexfloating)
+    real_dtype = np.dtype(dtype.char.lower()) if is_complex else dtype
+    width = int(np.prod(shape)) * (2 if is_complex else 1)
+    buf = np.zeros((per_rank, width), dtype=real_dtype)
+    for j, i in enumerate(mine):
+        buf[j] = np.ascontiguousarray(local[i]).view(real_dtype).reshape(-1)
+    send = torch.from_numpy(buf).to(device)
+    recv = [torch.empty_like(send) for _ in range(ws)]
+    d.all_gather(recv, send)
+    out = [None] * n_units
+    for r in range(ws):
+        block = recv[r].cpu().numpy()
+        for j, i in enumerate(shard_units(n_units, r, ws)):
+            row = block[j]
+            out[i] = (row.view(dtype) if is_complex else row).reshape(shape).copy()
+    return out
+
+
+def run_sharded(fn, units, *args, **kwargs):
+    """Apply ``fn(unit, *args, **kwargs) -> ndarray`` to this rank's shard and gather everything."""
+    mine = shard_units(len(units))
+    local = {i: fn(units[i], *args, **kwargs) for i in mine}
+    return gather_results(local, len(units))
