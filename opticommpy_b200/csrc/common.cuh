@@ -89,4 +89,24 @@ __device__ __forceinline__ float4 ldg4(const float2* p) {
 }
 __device__ __forceinline__ void stg4(float2* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// Streaming accesses that do not allocate in L1: the field arrays are touched once per kernel, while
+// the small twiddle tables must stay L1-resident (an L1 miss on a table load costs an L2 round trip in
+// the middle of a dependent FFT chain).
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+    float2 v;
+    asm("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float2* p, float2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 }  // namespace ocb

@@ -43,7 +43,11 @@ int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, i
     return fail("fused engine: unsupported N2", __FILE__, __LINE__);
 }
 int launch_linop_perm(ocb_ssfm_plan* p, float2* LP, double a, double b, double Fs, double h, double scale,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool split = false) {
+    if (split) {
+        OCB_LAUNCH(k_tab_linop_perm_s, grid_for(p->N, 256, 1), 256, 0, st, LP, kFreqC, p->N, a, b, Fs, h, scale);
+        return 0;
+    }
     OCB_LAUNCH(k_tab_linop_perm, grid_for(p->N, 256, 1), 256, 0, st, LP, p->q1, p->q2, kFreqC, p->N, a, b, Fs, h, scale);
     return 0;
 }
@@ -68,6 +72,25 @@ int fused_init_tables(ocb_ssfm_plan* p, cudaStream_t st) {
     return 0;
 }
 
+// pair-split kernels (N1 = N2 = 1024, both polarisations)
+template <int MODE>
+int launch_time_s(const TimeArgs& a, cudaStream_t st) {
+    OCB_LAUNCH((k_time_s<MODE>), a.N2, 128, 0, st, a);
+    return 0;
+}
+int launch_freq_s(float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st,
+                  const long long* flag = nullptr, long long step_id = 0) {
+    static bool configured = false;
+    constexpr int C = kFreqC;
+    const size_t smem = (size_t)2 * 32 * (32 * C + 16) * sizeof(float);
+    if (!configured) {
+        OCB_CUDA(cudaFuncSetAttribute(k_freq_s<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    OCB_LAUNCH((k_freq_s<C>), NP * N1 / C, 64 * C, smem, st, W, LP, tw, N1, flag, step_id);
+    return 0;
+}
+
 TimeArgs time_base(ocb_ssfm_plan* p) {
     TimeArgs a{};
     a.tw = p->tw1; a.tabV = p->tabV; a.tabU = p->tabU;
@@ -87,6 +110,7 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
     const double a = -dir * q->alpha_lin / 2.0, b = dir * q->beta2 / 2.0;
     const size_t field_bytes = (size_t)R * N * sizeof(float2);
     if (fused_init_tables(p, st)) return 1;
+    const bool split = p->split;
     float2* bufs[3] = {p->A, p->B, p->Cb};
     float2* Wb = p->G;
     float2* LP = p->T1;
@@ -96,6 +120,19 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
     int next_save = 0;
     uint64_t amp_calls = 0;
 
+    // keep the operator tables (read by every k_freq launch) resident in L2
+    {
+        static bool limit_set = false;
+        if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 32u << 20); limit_set = true; }
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = p->T1;
+        attr.accessPolicyWindow.num_bytes = (size_t)((char*)p->Pch - (char*)p->T1);  // T1 and T2
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);  // best effort
+        cudaGetLastError();
+    }
     if (launch_transpose(p, (const float2*)rows_inout, bufs[0], R, true, 1.0f, st)) return 1;
     const float2* noiseT = nullptr;
     if (q->direction > 0 && q->amp_mode == OCB_AMP_EDFA && q->noise_mode == OCB_NOISE_INJECTED) {
@@ -124,7 +161,7 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 hz_ = q->hz;
             }
             if (!(table_h == hz_)) {
-                if (launch_linop_perm(p, LP, a, b, q->Fs, hz_ / 2.0, 1.0 / (double)N, st)) return 1;
+                if (launch_linop_perm(p, LP, a, b, q->Fs, hz_ / 2.0, 1.0 / (double)N, st, split)) return 1;
                 table_h = hz_;
             }
             // first half step (channels.py:409-410): time pass forward, frequency pass with L, then the
@@ -133,15 +170,15 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 ProfScope ps(p, 2, st);
                 TimeArgs c0 = time_base(p);
                 c0.in = bufs[cur]; c0.out = Wb;
-                if (launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
-                if (launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st)) return 1;
+                if (split ? launch_time_s<TM_FWD>(c0, st) : launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
+                if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st) : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st)) return 1;
             }
             {
                 ProfScope ps(p, 1, st);
                 TimeArgs c1 = time_base(p);
                 c1.in = Wb; c1.out = Wb; c1.aux0 = bufs[cur]; c1.aux1 = p->Ehd; c1.pch = p->Pch;
                 c1.cphi = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma);
-                if (launch_time<2, TM_FIRST>(p->q1, c1, st)) return 1;
+                if (split ? launch_time_s<TM_FIRST>(c1, st) : launch_time<2, TM_FIRST>(p->q1, c1, st)) return 1;
             }
             int ec = cur, dst = (cur + 1) % 3;
             // Fixed-point loop (channels.py:413).  Iteration it+1 is enqueued BEFORE the outcome of
@@ -153,7 +190,8 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
             auto enqueue_iter = [&](int e_c, int d_st, unsigned long long seq) -> int {
                 {
                     ProfScope ps(p, 2, st);
-                    if (launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, p->conv_flag, step_id)) return 1;  // :420-421
+                    if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st, p->conv_flag, step_id)
+                              : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, p->conv_flag, step_id)) return 1;  // :420-421
                 }
                 ProfScope ps(p, 0, st);
                 TimeArgs ci = time_base(p);
@@ -161,7 +199,7 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 ci.cphi = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma * 0.5);
                 ci.ext.mail = p->d_mail; ci.ext.converged_step = p->conv_flag; ci.ext.step_id = step_id;
                 ci.ext.seq = seq; ci.ext.tol = q->tol;
-                return launch_time<2, TM_ITER>(p->q1, ci, st);  // :424, :436, :414-417
+                return split ? launch_time_s<TM_ITER>(ci, st) : launch_time<2, TM_ITER>(p->q1, ci, st);  // :424, :436, :414-417
             };
             unsigned long long seq_cur = ++p->mail_seq;
             if (enqueue_iter(ec, dst, seq_cur)) return 1;

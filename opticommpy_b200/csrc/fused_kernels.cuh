@@ -119,11 +119,11 @@ k_time(const TimeArgs A) {
     if constexpr (MODE == TM_FWD) {
         const float2* src = A.in + base;
 #pragma unroll
-        for (int a = 0; a < 32; ++a) v[a] = __ldg(src + Q1 * a + t);
+        for (int a = 0; a < 32; ++a) v[a] = ld_stream(src + Q1 * a + t);
     } else {
         const float2* src = A.in + base;
 #pragma unroll
-        for (int s = 0; s < 32; ++s) v[s] = __ldg(src + s * Q1 + t);
+        for (int s = 0; s < 32; ++s) v[s] = ld_stream(src + s * Q1 + t);
         static_for<0, G>([&](auto gg) {
             constexpr int GI = decltype(gg)::value;
             static_for<0, Q1>([&](auto kk) {
@@ -141,7 +141,7 @@ k_time(const TimeArgs A) {
     if constexpr (MODE == TM_INV) {
         float2* dst = A.out + base;
 #pragma unroll
-        for (int a = 0; a < 32; ++a) dst[Q1 * a + t] = make_float2(v[a].x * A.out_scale, v[a].y * A.out_scale);
+        for (int a = 0; a < 32; ++a) st_stream(dst + Q1 * a + t, make_float2(v[a].x * A.out_scale, v[a].y * A.out_scale));
         return;
     }
     if constexpr (MODE == TM_NLSE) {  // channels.py:225
@@ -158,8 +158,8 @@ k_time(const TimeArgs A) {
             const float2* ech = A.aux0 + base;
 #pragma unroll
             for (int a = 0; a < 32; ++a) {
-                ehd_out[Q1 * a + t] = v[a];
-                pown[Q1 * a + t] = cabs2(__ldg(ech + Q1 * a + t));
+                st_stream(ehd_out + Q1 * a + t, v[a]);
+                pown[Q1 * a + t] = cabs2(ld_stream(ech + Q1 * a + t));
             }
         } else {
             // v = E_fd: convergence sums against the previous iterate, store as the new iterate
@@ -167,10 +167,10 @@ k_time(const TimeArgs A) {
             float2* ec_new = A.aux1 + base;
 #pragma unroll
             for (int a = 0; a < 32; ++a) {
-                const float2 e = __ldg(ec + Q1 * a + t);
+                const float2 e = ld_stream(ec + Q1 * a + t);
                 s_num += cabs2(make_float2(v[a].x - e.x, v[a].y - e.y));  // channels.py:517
                 s_den += cabs2(e);
-                ec_new[Q1 * a + t] = v[a];
+                st_stream(ec_new + Q1 * a + t, v[a]);
                 pown[Q1 * a + t] = cabs2(v[a]);
             }
         }
@@ -182,12 +182,12 @@ k_time(const TimeArgs A) {
             const float P = pown[Q1 * a + t] + poth[Q1 * a + t];
             float ph;
             if constexpr (MODE == TM_FIRST) {
-                if (pol == 0) pch[Q1 * a + t] = P;
+                if (pol == 0) st_stream(pch + Q1 * a + t, P);
                 ph = A.cphi * P;  // φ = (8/9)γ(P+P)/2, channels.py:390/493 with E_conv == Ech
             } else {
                 s_max = fmaxf(s_max, P);
-                ph = A.cphi * (__ldg(pch + Q1 * a + t) + P);  // channels.py:436
-                v[a] = __ldg(ehd + Q1 * a + t);
+                ph = A.cphi * (ld_stream(pch + Q1 * a + t) + P);  // channels.py:436
+                v[a] = ld_stream(ehd + Q1 * a + t);
             }
             v[a] = cmul(v[a], phase_rot(ph));  // channels.py:414-417
         }
@@ -202,7 +202,7 @@ k_time(const TimeArgs A) {
             static_for<0, Q1>([&](auto kk) {
                 constexpr int KQ = decltype(kk)::value, SLOT = GI * Q1 + brev<Q1>(KQ);
                 const float2 w = cmul(wV[GI], __ldg(Urow + KQ));
-                dst[SLOT * Q1 + t] = cmul(v[SLOT], w);
+                st_stream(dst + SLOT * Q1 + t, cmul(v[SLOT], w));
             });
         });
     }
@@ -235,16 +235,23 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
     const float2* lp = LP + (int64_t)tile * 32 * (Q2 * C) + q * C + c;
     auto bsync = [] { __syncthreads(); };
 
+    // the tile's slice of the operator table (32 x Q2*C entries) is needed after the forward transform:
+    // start its HBM->L2 fetch now (one 128-byte line per thread and trip)
+    {
+        const char* lp_tile = reinterpret_cast<const char*>(LP + (int64_t)tile * 32 * (Q2 * C));
+        constexpr int LINES = 32 * Q2 * C * 8 / 128;
+        for (int l = tid; l < LINES; l += Q2 * C) prefetch_l2(lp_tile + l * 128);
+    }
     float2 v[32];
 #pragma unroll
-    for (int a = 0; a < 32; ++a) v[a] = base[(int64_t)(Q2 * a + q) * N1];
+    for (int a = 0; a < 32; ++a) v[a] = ld_stream(base + (int64_t)(Q2 * a + q) * N1);
     coop_fft_forward<Q2, C, C>(v, xr, xi, tw, q, c, bsync);
 #pragma unroll
-    for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], __ldg(lp + s * (Q2 * C)));
+    for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], ld_stream(lp + s * (Q2 * C)));
     __syncthreads();
     coop_fft_inverse<Q2, C, C>(v, xr, xi, tw, q, c, bsync);
 #pragma unroll
-    for (int a = 0; a < 32; ++a) base[(int64_t)(Q2 * a + q) * N1] = v[a];
+    for (int a = 0; a < 32; ++a) st_stream(base + (int64_t)(Q2 * a + q) * N1, v[a]);
 }
 
 // ------------------------------------------------------------------------------------------

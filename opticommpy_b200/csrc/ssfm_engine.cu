@@ -5,6 +5,7 @@
 // Reference control flow restated here (not code): optic/models/channels.py:380-456
 // (manakovSSF), optic/dsp/equalization.py:1088-1161 (manakovDBP), channels.py:215-238 (ssfm).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -12,6 +13,7 @@
 #include "../../include/opticomm_b200.h"
 #include "ssfm_kernels.cuh"
 #include "fused_kernels.cuh"
+#include "fused_split_kernels.cuh"
 
 using namespace ocb;
 
@@ -62,6 +64,7 @@ struct ocb_ssfm_plan {
     // fused four-step engine (power-of-two N = (32 q1) x (32 q2), single pol-pair): geometry + tables
     int engine = 0;       // OCB_ENGINE_*: 0 auto, 1 cuFFT, 2 fused
     bool fused_ok = false, fused_tables_ready = false;
+    bool split = false;   // pair-split kernels (16 samples per thread) for N1 = N2 = 1024, one pol-pair
     int q1 = 0, q2 = 0;
     float2 *tw1 = nullptr, *tw2 = nullptr, *tabV = nullptr, *tabU = nullptr;
     float2 *Cb = nullptr, *Nb = nullptr;  // third rotating field buffer, engine-layout noise copy
@@ -124,6 +127,7 @@ extern "C" int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out) {
     p->N = N;
     p->rows = rows;
     p->fused_ok = (rows == 1 || rows == 2) && fused_geometry(N, &p->q1, &p->q2);
+    p->split = p->fused_ok && rows == 2 && p->q1 == 32 && p->q2 == 32 && getenv("OCB_SPLIT") != nullptr;
     if (cufftCreate(&p->fft) != CUFFT_SUCCESS) { delete p; return fail("cufftCreate failed", __FILE__, __LINE__); }
     p->fft_ok = true;
     if (cufftSetAutoAllocation(p->fft, 0) != CUFFT_SUCCESS) { ocb_ssfm_plan_destroy(p); return fail("cufftSetAutoAllocation failed", __FILE__, __LINE__); }
