@@ -127,23 +127,42 @@ extern "C" int ocb_edc_run(const void* x_rows, void* y_rows, int64_t L, int nMod
 }
 
 // =============================================================================================
-// Adaptive MIMO equalizer: one persistent warp per independent stream.  Lane l owns taps
-// t = l + 32 j (j < TPL) of all NM*NM sub-filters in registers; the per-symbol dot products are
-// butterfly-reduced with warp shuffles; the tap update stays in registers.
+// Adaptive MIMO equalizer: LPS lanes per independent stream (8 for <= 32 taps), each lane owning
+// taps t = l + LPS*j (j < TPL) of all NM*NM sub-filters in registers.  The input samples of a chunk of
+// symbols are staged in shared memory by cp.async (double buffered), so that the per-symbol critical
+// path is: smem window read -> FMAs -> log2(LPS) shuffle stages -> error term -> tap update.
 // Tap layout: H[(m + n*NM), t] = tap t from input mode n to output mode m (equalization.py:467).
 // =============================================================================================
 namespace {
 
-template <int NM, int TPL, bool WL>
+constexpr int kEqChunk = 128;  // symbols per staged chunk
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int NM, int TPL, int LPS, bool WL>
 __global__ void __launch_bounds__(128)
 k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* __restrict__ Hg,
           float2* __restrict__ HWg, float2* __restrict__ Y, float* __restrict__ ERR, float2* __restrict__ HIT,
           int nStreams, int64_t xStride, int64_t refStride, int64_t yStride, int64_t errStride,
           int64_t errModeStride, int64_t L, int nTaps, int SpS, int alg, float mu,
           const float2* __restrict__ constSymb, int M, const float* __restrict__ radii, int nR, float Rcma) {
-    const int lane = threadIdx.x & 31;
-    const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (stream >= nStreams) return;
+    constexpr int SPW = 32 / LPS;  // streams per warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPS, l = lane % LPS;
+    const int slot = warp * SPW + sub;  // stream slot inside the CTA
+    const int stream_raw = blockIdx.x * ((blockDim.x >> 5) * SPW) + slot;
+    const bool live = stream_raw < nStreams;          // dead slots shadow the last stream, never store
+    const int stream = live ? stream_raw : nStreams - 1;
+    const int rows_chunk = (kEqChunk - 1) * SpS + nTaps;
+    float2* xbuf = reinterpret_cast<float2*>(smem_raw) + (size_t)slot * 2 * (rows_chunk * NM + kEqChunk * NM);
+    float2* rbuf = xbuf + 2 * rows_chunk * NM;  // [2][kEqChunk*NM] reference symbols
+
     const float2* x = X + (int64_t)stream * xStride;
     const float2* ref = REF ? REF + (int64_t)stream * refStride : nullptr;
     float2* Hs = Hg + (int64_t)stream * NM * NM * nTaps;
@@ -157,194 +176,236 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
     for (int r = 0; r < NM * NM; ++r)
 #pragma unroll
         for (int j = 0; j < TPL; ++j) {
-            int t = lane + 32 * j;
+            const int t = l + LPS * j;
             H[r][j] = t < nTaps ? Hs[r * nTaps + t] : make_float2(0.f, 0.f);
             if (WL) HW[r][j] = t < nTaps ? HWs[r * nTaps + t] : make_float2(0.f, 0.f);
         }
 
-    auto load_window = [&](int64_t ind, float2 (&w)[NM][TPL]) {
-#pragma unroll
-        for (int j = 0; j < TPL; ++j) {
-            int t = lane + 32 * j;
-            const float2* p = x + (ind * SpS + t) * NM;
-#pragma unroll
-            for (int n = 0; n < NM; ++n) w[n][j] = (t < nTaps) ? __ldg(p + n) : make_float2(0.f, 0.f);
+    // stage chunk k (symbols [k*CH, min(L, (k+1)*CH))) into buffer k&1
+    auto stage = [&](int64_t k) {
+        const int64_t s0 = k * kEqChunk;
+        if (s0 >= L) return;
+        const int nsym = (int)((L - s0) < kEqChunk ? (L - s0) : kEqChunk);
+        const int rows = (nsym - 1) * SpS + nTaps;
+        float2* dst = xbuf + (k & 1) * rows_chunk * NM;
+        const float2* src = x + s0 * SpS * NM;
+        for (int i = l; i < rows * NM; i += LPS) cp_async8(dst + i, src + i);
+        if (ref) {
+            float2* rd = rbuf + (k & 1) * kEqChunk * NM;
+            const float2* rs = ref + s0 * NM;
+            for (int i = l; i < nsym * NM; i += LPS) cp_async8(rd + i, rs + i);
         }
     };
 
-    float2 w[NM][TPL], wn[NM][TPL];
-    if (L > 0) load_window(0, w);
     float prev_err[NM];
 #pragma unroll
     for (int m = 0; m < NM; ++m) prev_err[m] = 0.f;
+    constexpr int kMaxR = 8;  // radii kept in registers (16/64-QAM have 3/9 rings; more fall back to memory)
+    float rad[kMaxR];
+#pragma unroll
+    for (int i = 0; i < kMaxR; ++i) rad[i] = (radii && i < nR) ? radii[i] : 3.0e38f;
 
-    for (int64_t ind = 0; ind < L; ++ind) {
-        if (ind + 1 < L) load_window(ind + 1, wn);  // prefetch: independent of the tap recurrence
+    stage(0);
+    cp_async_commit();
+    const int64_t nchunks = (L + kEqChunk - 1) / kEqChunk;
+    for (int64_t k = 0; k < nchunks; ++k) {
+        cp_async_wait_all();
+        __syncwarp();
+        stage(k + 1);  // lands while this chunk is processed
+        cp_async_commit();
+        const float2* xb = xbuf + (k & 1) * rows_chunk * NM;
+        const float2* rb = rbuf + (k & 1) * kEqChunk * NM;
+        const int64_t s0 = k * kEqChunk;
+        const int nsym = (int)((L - s0) < kEqChunk ? (L - s0) : kEqChunk);
 
-        // ---- filter: out[m] = Σ_n H[m + n NM, :] · x_n[window]   (equalization.py:464-471)
-        float2 o[NM];
-        float nrm[NM];
+        for (int s = 0; s < nsym; ++s) {
+            const int64_t ind = s0 + s;
+            float2 w[NM][TPL];
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            float2 acc = make_float2(0.f, 0.f);
+            for (int j = 0; j < TPL; ++j) {
+                const int t = l + LPS * j;
+                const float2* p = xb + (s * SpS + t) * NM;
 #pragma unroll
-            for (int n = 0; n < NM; ++n)
-#pragma unroll
-                for (int j = 0; j < TPL; ++j) {
-                    float2 p = cmul(H[m + n * NM][j], w[n][j]);
-                    acc.x += p.x; acc.y += p.y;
-                    if (WL) {
-                        float2 q = cmul_conj(HW[m + n * NM][j], w[n][j]);  // H_ · conj(x)
-                        acc.x += q.x; acc.y += q.y;
-                    }
-                }
-            o[m] = acc;
-        }
-        if (alg == OCB_ALG_NLMS) {
-#pragma unroll
-            for (int n = 0; n < NM; ++n) {
-                float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < TPL; ++j) s += cabs2(w[n][j]);
-                nrm[n] = s;
+                for (int n = 0; n < NM; ++n) w[n][j] = (t < nTaps) ? p[n] : make_float2(0.f, 0.f);
             }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
+            // ---- filter: out[m] = sum_n H[m + n NM, :] . x_n[window]   (equalization.py:464-471)
+            float2 o[NM];
+            float nrm[NM];
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
-                o[m].x += __shfl_xor_sync(0xffffffffu, o[m].x, off);
-                o[m].y += __shfl_xor_sync(0xffffffffu, o[m].y, off);
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int n = 0; n < NM; ++n)
+#pragma unroll
+                    for (int j = 0; j < TPL; ++j) {
+                        float2 pr = cmul(H[m + n * NM][j], w[n][j]);
+                        acc.x += pr.x; acc.y += pr.y;
+                        if (WL) {
+                            float2 qq = cmul_conj(HW[m + n * NM][j], w[n][j]);  // H_ . conj(x)
+                            acc.x += qq.x; acc.y += qq.y;
+                        }
+                    }
+                o[m] = acc;
             }
             if (alg == OCB_ALG_NLMS) {
 #pragma unroll
-                for (int n = 0; n < NM; ++n) nrm[n] += __shfl_xor_sync(0xffffffffu, nrm[n], off);
+                for (int n = 0; n < NM; ++n) {
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < TPL; ++j) sacc += cabs2(w[n][j]);
+                    nrm[n] = sacc;
+                }
             }
-        }
-        if (lane < NM) {
-            float2 sel = o[0];
 #pragma unroll
-            for (int m = 1; m < NM; ++m) if (lane == m) sel = o[m];
-            y[ind * NM + lane] = sel;  // equalization.py:473
-        }
-
-        // ---- error term g_m and squared error, per algorithm
-        float2 g[NM];
-        float esq[NM];
+            for (int off = LPS / 2; off > 0; off >>= 1) {
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            const float a2 = cabs2(o[m]);
-            if (alg == OCB_ALG_CMA) {  // :826-829
-                float e = Rcma - a2;
-                g[m] = make_float2(e * o[m].x, e * o[m].y);
-                esq[m] = e * e;
-            } else if (alg == OCB_ALG_RDE || alg == OCB_ALG_DARDE) {  // :887-894, :953-959
-                float Rd;
-                if (alg == OCB_ALG_RDE) {
-                    float r = sqrtf(a2);
-                    float best = fabsf(radii[0] - r);
-                    Rd = radii[0];
-                    for (int i = 1; i < nR; ++i) {
-                        float dd = fabsf(radii[i] - r);
-                        if (dd < best) { best = dd; Rd = radii[i]; }
-                    }
-                } else {
-                    float2 s = __ldg(ref + ind * NM + m);
-                    Rd = sqrtf(cabs2(s));
+                for (int m = 0; m < NM; ++m) {
+                    o[m].x += __shfl_xor_sync(0xffffffffu, o[m].x, off);
+                    o[m].y += __shfl_xor_sync(0xffffffffu, o[m].y, off);
                 }
-                float e = Rd * Rd - a2;
-                g[m] = make_float2(e * o[m].x, e * o[m].y);
-                esq[m] = e * e;
-            } else if (alg == OCB_ALG_NLMS) {  // :556
-                float2 s = __ldg(ref + ind * NM + m);
-                g[m] = make_float2(s.x - o[m].x, s.y - o[m].y);
-                esq[m] = cabs2(g[m]);
-            } else if (alg == OCB_ALG_DDLMS) {  // :688-691  nearest constellation point, first index on ties
-                float best = 3.4e38f;
-                int bi = 0x7fffffff;
-                for (int c = lane; c < M; c += 32) {
-                    float2 s = __ldg(constSymb + c);
-                    float dd = cabs2(make_float2(o[m].x - s.x, o[m].y - s.y));
-                    if (dd < best) { best = dd; bi = c; }
-                }
+                if (alg == OCB_ALG_NLMS) {
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    float ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    for (int n = 0; n < NM; ++n) nrm[n] += __shfl_xor_sync(0xffffffffu, nrm[n], off);
                 }
-                float2 s = __ldg(constSymb + bi);
-                g[m] = make_float2(s.x - o[m].x, s.y - o[m].y);
-                esq[m] = cabs2(g[m]);
-            } else {  // static: no update (:505-506)
-                g[m] = make_float2(0.f, 0.f);
-                esq[m] = prev_err[m];
             }
-            prev_err[m] = esq[m];
-        }
-        if (lane < NM) {
-            float sel = esq[0];
+            if (live && l < NM) {
+                float2 sel = o[0];
 #pragma unroll
-            for (int m = 1; m < NM; ++m) if (lane == m) sel = esq[m];
-            err[(int64_t)lane * errModeStride + ind] = sel;
-        }
+                for (int m = 1; m < NM; ++m) if (l == m) sel = o[m];
+                y[ind * NM + l] = sel;  // equalization.py:473
+            }
 
-        // ---- tap update: H[m + n NM, :] += mu g_m conj(x_n)   (:838-840 and siblings)
-        if (alg != OCB_ALG_STATIC) {
+            // ---- error term g_m and squared error, per algorithm
+            float2 g[NM];
+            float esq[NM];
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
-                const float2 wg = make_float2(mu * g[m].x, mu * g[m].y);
+                const float a2 = cabs2(o[m]);
+                if (alg == OCB_ALG_CMA) {  // :826-829
+                    float e = Rcma - a2;
+                    g[m] = make_float2(e * o[m].x, e * o[m].y);
+                    esq[m] = e * e;
+                } else if (alg == OCB_ALG_RDE || alg == OCB_ALG_DARDE) {  // :887-894, :953-959
+                    float Rd;
+                    if (alg == OCB_ALG_RDE) {
+                        float r = sqrtf(a2);
+                        float best = fabsf(rad[0] - r);
+                        Rd = rad[0];
 #pragma unroll
-                for (int n = 0; n < NM; ++n) {
-                    const float inv = (alg == OCB_ALG_NLMS) ? 1.0f / nrm[n] : 1.0f;
+                        for (int i = 1; i < kMaxR; ++i) {
+                            float dd = fabsf(rad[i] - r);
+                            if (dd < best) { best = dd; Rd = rad[i]; }
+                        }
+                        for (int i = kMaxR; i < nR; ++i) {
+                            float dd = fabsf(radii[i] - r);
+                            if (dd < best) { best = dd; Rd = radii[i]; }
+                        }
+                    } else {
+                        Rd = sqrtf(cabs2(rb[s * NM + m]));
+                    }
+                    float e = Rd * Rd - a2;
+                    g[m] = make_float2(e * o[m].x, e * o[m].y);
+                    esq[m] = e * e;
+                } else if (alg == OCB_ALG_NLMS) {  // :556
+                    float2 sr = rb[s * NM + m];
+                    g[m] = make_float2(sr.x - o[m].x, sr.y - o[m].y);
+                    esq[m] = cabs2(g[m]);
+                } else if (alg == OCB_ALG_DDLMS) {  // :688-691  nearest constellation point, first index on ties
+                    float best = 3.4e38f;
+                    int bi = 0x7fffffff;
+                    for (int c = l; c < M; c += LPS) {
+                        float2 sc = __ldg(constSymb + c);
+                        float dd = cabs2(make_float2(o[m].x - sc.x, o[m].y - sc.y));
+                        if (dd < best) { best = dd; bi = c; }
+                    }
 #pragma unroll
-                    for (int j = 0; j < TPL; ++j) {
-                        float2 xin = w[n][j];
-                        if (alg == OCB_ALG_NLMS) { xin.x *= inv; xin.y *= inv; }  // :563
-                        float2 u = cmul_conj(wg, xin);
-                        H[m + n * NM][j].x += u.x; H[m + n * NM][j].y += u.y;
-                        if (WL) {
-                            float2 v = cmul(wg, xin);
-                            HW[m + n * NM][j].x += v.x; HW[m + n * NM][j].y += v.y;
+                    for (int off = LPS / 2; off > 0; off >>= 1) {
+                        float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    }
+                    float2 sc = __ldg(constSymb + bi);
+                    g[m] = make_float2(sc.x - o[m].x, sc.y - o[m].y);
+                    esq[m] = cabs2(g[m]);
+                } else {  // static: no update (:505-506)
+                    g[m] = make_float2(0.f, 0.f);
+                    esq[m] = prev_err[m];
+                }
+                prev_err[m] = esq[m];
+            }
+            if (live && l < NM) {
+                float sel = esq[0];
+#pragma unroll
+                for (int m = 1; m < NM; ++m) if (l == m) sel = esq[m];
+                err[(int64_t)l * errModeStride + ind] = sel;
+            }
+
+            // ---- tap update: H[m + n NM, :] += mu g_m conj(x_n)   (:838-840 and siblings)
+            if (alg != OCB_ALG_STATIC) {
+#pragma unroll
+                for (int m = 0; m < NM; ++m) {
+                    const float2 wg = make_float2(mu * g[m].x, mu * g[m].y);
+#pragma unroll
+                    for (int n = 0; n < NM; ++n) {
+                        const float inv = (alg == OCB_ALG_NLMS) ? 1.0f / nrm[n] : 1.0f;
+#pragma unroll
+                        for (int j = 0; j < TPL; ++j) {
+                            float2 xin = w[n][j];
+                            if (alg == OCB_ALG_NLMS) { xin.x *= inv; xin.y *= inv; }  // :563
+                            float2 u = cmul_conj(wg, xin);
+                            H[m + n * NM][j].x += u.x; H[m + n * NM][j].y += u.y;
+                            if (WL) {
+                                float2 vv = cmul(wg, xin);
+                                HW[m + n * NM][j].x += vv.x; HW[m + n * NM][j].y += vv.y;
+                            }
                         }
                     }
                 }
             }
-        }
-        if (hit) {  // storeCoeff (:511-512): Hiter[:, :, ind] = H, stored as (L, NM², nTaps)
+            if (hit && live) {  // storeCoeff (:511-512): Hiter[:, :, ind] = H, stored as (L, NM^2, nTaps)
 #pragma unroll
-            for (int r = 0; r < NM * NM; ++r)
+                for (int r = 0; r < NM * NM; ++r)
 #pragma unroll
-                for (int j = 0; j < TPL; ++j) {
-                    int t = lane + 32 * j;
-                    if (t < nTaps) hit[(ind * NM * NM + r) * nTaps + t] = H[r][j];
-                }
-        }
-#pragma unroll
-        for (int n = 0; n < NM; ++n)
-#pragma unroll
-            for (int j = 0; j < TPL; ++j) w[n][j] = wn[n][j];
-    }
-
-#pragma unroll
-    for (int r = 0; r < NM * NM; ++r)
-#pragma unroll
-        for (int j = 0; j < TPL; ++j) {
-            int t = lane + 32 * j;
-            if (t < nTaps) {
-                Hs[r * nTaps + t] = H[r][j];
-                if (WL) HWs[r * nTaps + t] = HW[r][j];
+                    for (int j = 0; j < TPL; ++j) {
+                        const int t = l + LPS * j;
+                        if (t < nTaps) hit[(ind * NM * NM + r) * nTaps + t] = H[r][j];
+                    }
             }
         }
+    }
+    cp_async_wait_all();
+
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < NM * NM; ++r)
+#pragma unroll
+            for (int j = 0; j < TPL; ++j) {
+                const int t = l + LPS * j;
+                if (t < nTaps) {
+                    Hs[r * nTaps + t] = H[r][j];
+                    if (WL) HWs[r * nTaps + t] = HW[r][j];
+                }
+            }
+    }
 }
 
-template <int NM, int TPL>
-int launch_mimo(bool wl, int grid, int block, cudaStream_t st, const float2* X, const float2* REF, float2* H,
+template <int NM, int TPL, int LPS>
+int launch_mimo(bool wl, cudaStream_t st, const float2* X, const float2* REF, float2* H,
                 float2* HW, float2* Y, float* ERR, float2* HIT, int nStreams, int64_t xs, int64_t rs, int64_t ys,
                 int64_t es, int64_t ems, int64_t L, int nTaps,
                 int SpS, int alg, float mu, const float2* cs, int M, const float* radii, int nR, float Rcma) {
-    if (wl) OCB_LAUNCH((k_mimo_eq<NM, TPL, true>), grid, block, 0, st, X, REF, H, HW, Y, ERR, HIT, nStreams, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
-    else OCB_LAUNCH((k_mimo_eq<NM, TPL, false>), grid, block, 0, st, X, REF, H, HW, Y, ERR, HIT, nStreams, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
+    constexpr int SPB = 32 / LPS;  // streams per one-warp CTA (keeps the staged chunks of a CTA small)
+    const int grid = (nStreams + SPB - 1) / SPB;
+    const int rows_chunk = (kEqChunk - 1) * SpS + nTaps;
+    const size_t smem = (size_t)SPB * 2 * ((size_t)rows_chunk * NM + kEqChunk * NM) * sizeof(float2);
+    OCB_REQUIRE(smem <= 200 * 1024, "mimo_eq_run: SpS/nTaps too large for the staged input chunk");
+    if (wl) {
+        OCB_CUDA(cudaFuncSetAttribute(k_mimo_eq<NM, TPL, LPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OCB_LAUNCH((k_mimo_eq<NM, TPL, LPS, true>), grid, 32, smem, st, X, REF, H, HW, Y, ERR, HIT, nStreams, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
+    } else {
+        OCB_CUDA(cudaFuncSetAttribute(k_mimo_eq<NM, TPL, LPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OCB_LAUNCH((k_mimo_eq<NM, TPL, LPS, false>), grid, 32, smem, st, X, REF, H, HW, Y, ERR, HIT, nStreams, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
+    }
     return 0;
 }
 
@@ -370,20 +431,25 @@ extern "C" int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hw
     if (runWL) OCB_REQUIRE(Hwl != nullptr, "mimo_eq_run: runWL needs the augmented taps H_");
     if (L == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const int wpb = nStreams >= 4 * kNumSMs ? 4 : 1;  // warps (streams) per CTA
-    const int grid = (nStreams + wpb - 1) / wpb, block = 32 * wpb;
-    const int tpl = (nTaps + 31) / 32;
-#define OCB_MIMO_CASE(NM_, TPL_)                                                                               \
-    if (nModes == NM_ && tpl == TPL_)                                                                          \
-        return launch_mimo<NM_, TPL_>(runWL != 0, grid, block, st, (const float2*)x, (const float2*)ref,       \
-                                      (float2*)H, (float2*)Hwl, (float2*)y, (float*)errSq, (float2*)Hiter,     \
-                                      nStreams, x_stream_stride, ref_stream_stride, y_stream_stride,           \
-                                      err_stream_stride, err_mode_stride, L, nTaps, SpS, alg, mu,              \
-                                      (const float2*)constSymb, M,                                             \
-                                      (const float*)radii, nR, Rcma);
-    OCB_MIMO_CASE(1, 1) OCB_MIMO_CASE(1, 2) OCB_MIMO_CASE(1, 3) OCB_MIMO_CASE(1, 4)
-    OCB_MIMO_CASE(2, 1) OCB_MIMO_CASE(2, 2) OCB_MIMO_CASE(2, 3) OCB_MIMO_CASE(2, 4)
-    OCB_MIMO_CASE(4, 1) OCB_MIMO_CASE(4, 2)
+    // Lanes per stream.  Few streams (latency mode): a full warp per stream, one tap per lane when
+    // nTaps <= 32 — the per-symbol instruction count is what bounds a lone stream.  Many streams
+    // (throughput mode): 8 lanes x 4 taps, four streams per warp, 3 shuffle stages instead of 5.
+    const bool many = nStreams >= 4 * kNumSMs;
+    const int lps = (many && nTaps <= 32) ? 8 : ((many && nTaps <= 64) ? 16 : 32);
+    const int tpl = (nTaps + lps - 1) / lps;
+#define OCB_MIMO_CASE(NM_, TPL_, LPS_)                                                                         \
+    if (nModes == NM_ && lps == LPS_ && tpl == TPL_)                                                           \
+        return launch_mimo<NM_, TPL_, LPS_>(runWL != 0, st, (const float2*)x, (const float2*)ref,              \
+                                         (float2*)H, (float2*)Hwl, (float2*)y, (float*)errSq, (float2*)Hiter,  \
+                                         nStreams, x_stream_stride, ref_stream_stride, y_stream_stride,        \
+                                         err_stream_stride, err_mode_stride, L, nTaps, SpS, alg, mu,           \
+                                         (const float2*)constSymb, M, (const float*)radii, nR, Rcma);
+    OCB_MIMO_CASE(1, 1, 32) OCB_MIMO_CASE(1, 2, 32) OCB_MIMO_CASE(1, 3, 32) OCB_MIMO_CASE(1, 4, 32)
+    OCB_MIMO_CASE(2, 1, 32) OCB_MIMO_CASE(2, 2, 32) OCB_MIMO_CASE(2, 3, 32) OCB_MIMO_CASE(2, 4, 32)
+    OCB_MIMO_CASE(4, 1, 32) OCB_MIMO_CASE(4, 2, 32)
+    OCB_MIMO_CASE(1, 1, 8) OCB_MIMO_CASE(1, 2, 8) OCB_MIMO_CASE(1, 3, 8) OCB_MIMO_CASE(1, 4, 8)
+    OCB_MIMO_CASE(2, 1, 8) OCB_MIMO_CASE(2, 2, 8) OCB_MIMO_CASE(2, 3, 8) OCB_MIMO_CASE(2, 4, 8)
+    OCB_MIMO_CASE(1, 3, 16) OCB_MIMO_CASE(1, 4, 16) OCB_MIMO_CASE(2, 3, 16) OCB_MIMO_CASE(2, 4, 16)
 #undef OCB_MIMO_CASE
     return fail("mimo_eq_run: unsupported (nModes, nTaps) combination", __FILE__, __LINE__);
 }
