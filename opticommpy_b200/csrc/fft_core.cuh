@@ -110,7 +110,8 @@ __device__ __forceinline__ void fft_dit(float2* v) {
 // Exchange buffer: planar float arrays xr/xi of size 32*(Q*CP + PAD) per group, element
 // (ka, q, c) at ka*(Q*CP + PAD) + q*CP + c, where CP = number of column-threads interleaved
 // (1 for the row kernel) — conflict-free for both access directions.
-// tw: twiddle table TW[ka*Q + q] = exp(-2 pi i q ka / S) in shared memory.
+// tw: twiddle table TW[ka*Q + q] = exp(-2 pi i q ka / S), followed by its transpose TWT[q*32 + ka]
+// (32*Q entries each) so that both transform directions read it lane-contiguously.
 // ------------------------------------------------------------------------------------------
 template <int Q>
 struct Coop {
@@ -154,7 +155,8 @@ __device__ __forceinline__ void coop_fft_inverse(float2* v, float* xr, float* xi
         static_for<0, Q>([&](auto jj) {
             constexpr int J = decltype(jj)::value;  // q'
             float2 z = v[GI * Q + J];
-            const float2 w = tw[ka * Q + J];
+            // transposed copy of the table (tw + 32*Q): entry [J][ka], so that lanes (ka) are contiguous
+            const float2 w = tw[32 * Q + J * 32 + ka];
             z = cmul_conj(z, w);  // conj twiddle for the inverse
             xr[ka * STR + J * CP + c] = z.x;
             xi[ka * STR + J * CP + c] = z.y;

@@ -83,7 +83,7 @@ __device__ __forceinline__ void coop1024s_inverse(float2* v, float* xr, float* x
     static_for<0, 16>([&](auto mm) {
         constexpr int M = decltype(mm)::value;
         const int q = 16 * h + M;
-        const float2 z = cmul_conj(v[M], __ldg(tw + x * 32 + q));
+        const float2 z = cmul_conj(v[M], __ldg(tw + q * 32 + x));  // W^{x q} is symmetric: lane-contiguous read
         xr[x * STR + q * CP + c] = z.x;
         xi[x * STR + q * CP + c] = z.y;
     });

@@ -275,7 +275,7 @@ __global__ void k_transpose(const float2* __restrict__ in, float2* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // Table builders (float64 math, rounded once to float32).
 // ------------------------------------------------------------------------------------------
-// tw[ka*Q + q] = exp(-2 pi i q ka / (32 Q))
+// tw[ka*Q + q] = exp(-2 pi i q ka / (32 Q)), followed by the transposed copy tw[32Q + q*32 + ka]
 __global__ void k_tab_tw(float2* tw, int Q) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 32 * Q) return;
@@ -283,6 +283,7 @@ __global__ void k_tab_tw(float2* tw, int Q) {
     double s, c;
     sincospi(-2.0 * (double)(q * ka) / (double)(32 * Q), &s, &c);
     tw[i] = make_float2((float)c, (float)s);
+    tw[32 * Q + q * 32 + ka] = make_float2((float)c, (float)s);
 }
 // V[n2*32 + ka] = exp(-2 pi i n2 ka / N) ; U[n2*Q1 + kq] = exp(-2 pi i n2 32 kq / N)
 __global__ void k_tab_inter(float2* V, float2* U, int N2, int Q1, int64_t N) {

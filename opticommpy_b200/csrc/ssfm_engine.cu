@@ -105,7 +105,7 @@ static bool fused_geometry(int64_t N, int* q1, int* q2) {
 }
 static int64_t fused_table_bytes(const ocb_ssfm_plan* p) {
     if (!p->fused_ok) return 0;
-    return align_up(32ll * p->q1 * 8, 256) + align_up(32ll * p->q2 * 8, 256) +
+    return align_up(2 * 32ll * p->q1 * 8, 256) + align_up(2 * 32ll * p->q2 * 8, 256) +
            align_up(32ll * p->q2 * 32 * 8, 256) + align_up(32ll * p->q2 * p->q1 * 8, 256) +
            align_up((int64_t)p->rows * p->N * 8, 256) + align_up(p->N * 8, 256);
 }
@@ -183,8 +183,8 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
     p->fft_area = c; c += align_up((int64_t)p->fft_work, 256);
     if (p->fft_work > 0) OCB_CUFFT(cufftSetWorkArea(p->fft, p->fft_area));
     if (p->fused_ok) {
-        p->tw1 = (float2*)c; c += align_up(32ll * p->q1 * 8, 256);
-        p->tw2 = (float2*)c; c += align_up(32ll * p->q2 * 8, 256);
+        p->tw1 = (float2*)c; c += align_up(2 * 32ll * p->q1 * 8, 256);
+        p->tw2 = (float2*)c; c += align_up(2 * 32ll * p->q2 * 8, 256);
         p->tabV = (float2*)c; c += align_up(32ll * p->q2 * 32 * 8, 256);
         p->tabU = (float2*)c; c += align_up(32ll * p->q2 * p->q1 * 8, 256);
         p->Cb = (float2*)c; c += align_up((int64_t)p->rows * p->N * 8, 256);
