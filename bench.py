@@ -127,6 +127,77 @@ def cpu_oracle_rate(n_steps, n=N_SAMPLES, seed=0):
     return n * st["steps"] / dt / 1e6, st["steps"], st["iterations"], dt
 
 
+def nl_pass_microbench(torch, lib, _cabi, n=N_SAMPLES, reps=60):
+    """The standalone fused nonlinear-step kernel (k_manakov_nl<false,2>: convergence sums + Kerr phase +
+    rotation, 68 algorithmic bytes per 2-pol sample) timed alone with CUDA events.  Three buffer sets
+    (3 x 68 MB > L2) are cycled so that every launch streams from HBM."""
+    sets = []
+    for i in range(3):
+        g = torch.Generator(device="cuda").manual_seed(i)
+        mk = lambda: (torch.randn((2, n, 2), device="cuda", generator=g) * 0.03).contiguous()
+        sets.append(dict(ehd=mk(), efd=mk(), ec=mk(), pch=torch.rand((1, n), device="cuda", generator=g) * 1e-3,
+                         out=torch.empty((2, n, 2), device="cuda"), sums=torch.zeros(3, dtype=torch.float64, device="cuda")))
+    vp = C.c_void_p
+    st = vp(_cabi.stream_ptr(torch))
+
+    def launch(b):
+        _cabi.check(lib.ocb_manakov_nl_pass(vp(b["ehd"].data_ptr()), vp(b["efd"].data_ptr()), vp(b["ec"].data_ptr()),
+                                            vp(b["pch"].data_ptr()), vp(b["out"].data_ptr()), vp(b["sums"].data_ptr()),
+                                            n, 1, 1.3, 0.08, 1, st), "nl_pass")
+    for i in range(6):
+        launch(sets[i % 3])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        launch(sets[i % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3  # us per launch
+
+
+def cupy_standin_rate(torch, rows0, prm, n_steps=40):
+    """Stand-in for the reference's CuPy path (optic/models/modelsGPU.py:428-482), which cannot run here
+    (no cupy): the same loop op for op with torch.fft and separate elementwise torch ops — operator
+    rebuilt every step, four copies per iteration, host sync on `lim < tol` — on the same B200, complex64.
+    Reported for context only; it is not the product path."""
+    import math
+    Ex, Ey = rows0[0:1].clone(), rows0[1:2].clone()
+    n = Ex.shape[1]
+    alpha = prm.alpha / (10 * math.log10(math.e))
+    lam = 299792.458 / prm.Fc
+    beta2 = -(prm.D * lam**2) / (2 * math.pi * 299792.458)
+    w = 2 * math.pi * prm.Fs * torch.fft.fftfreq(n, device="cuda", dtype=torch.float64)
+    arg = (-(alpha / 2) + 1j * (beta2 / 2) * w**2).to(torch.complex64).reshape(1, -1)
+    g = prm.gamma
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Exc, Eyc = Ex.clone(), Ey.clone()
+    iters = 0
+    for _ in range(n_steps):
+        Pch = Ex * torch.conj(Ex) + Ey * torch.conj(Ey)
+        phi = ((8 / 9) * g * (Pch + Exc * torch.conj(Exc) + Eyc * torch.conj(Eyc)) / 2).real
+        hz = prm.hz
+        lin = torch.exp(arg * (hz / 2))
+        Exh = torch.fft.ifft(torch.fft.fft(Ex) * lin)
+        Eyh = torch.fft.ifft(torch.fft.fft(Ey) * lin)
+        for it in range(prm.maxIter):
+            rot = torch.exp(1j * phi * hz)
+            Exf = torch.fft.ifft(torch.fft.fft(Exh * rot) * lin)
+            Eyf = torch.fft.ifft(torch.fft.fft(Eyh * rot) * lin)
+            lim = torch.sqrt(torch.linalg.norm(Exf - Exc) ** 2 + torch.linalg.norm(Eyf - Eyc) ** 2) / \
+                torch.sqrt(torch.linalg.norm(Exc) ** 2 + torch.linalg.norm(Eyc) ** 2)
+            Exc, Eyc = Exf.clone(), Eyf.clone()
+            iters += 1
+            if float(lim) < prm.tol:  # device -> host sync, like the CuPy `if lim < tol`
+                break
+            phi = ((8 / 9) * g * (Pch + Exc * torch.conj(Exc) + Eyc * torch.conj(Eyc)) / 2).real
+        Ex, Ey = Exf.clone(), Eyf.clone()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return n * n_steps / dt / 1e6, iters / n_steps
+
+
 def _cpu_worker(args):
     n_steps, seed = args
     os.environ["OMP_NUM_THREADS"] = "1"
@@ -171,6 +242,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spans", type=int, default=10, help="spans per propagation (10 = cfg2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the NL-kernel microbench and the CuPy stand-in")
+    ap.add_argument("--nl-only", action="store_true", help="only time the standalone nonlinear-step kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -190,6 +263,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _cabi.lib()
     st = C.c_void_p(_cabi.stream_ptr(torch))
+    if args.nl_only:
+        us = nl_pass_microbench(torch, lib, _cabi)
+        print(json.dumps({"nl_pass_us": us, "GBps": 68.0 * N_SAMPLES / (us * 1e-6) / 1e9,
+                          "frac_of_measured_peak": 68.0 * N_SAMPLES / (us * 1e-6) / 1e9 / measured_hbm_peak()[0]}))
+        return
 
     prm = channel_param(args.spans)
     # ---- inputs: one independent realisation per rank, pinned on the host, pristine copy in HBM
@@ -306,6 +384,16 @@ def main():
                               "linear_half_step_avg_us": 1e3 * prof[4] / max(prof[5], 1),
                               "nl_first_avg_us": 1e3 * prof[2] / max(prof[3], 1)},
         }
+        if not args.no_extras:
+            us = nl_pass_microbench(torch, lib, _cabi)
+            a_nl = 68.0 * N_SAMPLES / (us * 1e-6) / 1e9
+            line["roofline_nl_step"] = {"kernel": "k_manakov_nl<false,2> (standalone fused nonlinear step, ocb_manakov_nl_pass)",
+                                        "bound": "hbm", "bytes_per_launch": 68.0 * N_SAMPLES, "avg_us": us, "achieved": a_nl,
+                                        "peak": peak, "unit": "GB/s", "frac": a_nl / peak,
+                                        "note": "3 rotating buffer sets (204 MB > L2), 60 launches, CUDA events"}
+            sr, si = cupy_standin_rate(torch, rows0, channel_param(1))
+            line["cupy_standin"] = {"value": sr, "unit": "Msamples/s", "mean_iterations": si,
+                                    "what": "op-for-op torch.fft restatement of optic/models/modelsGPU.py:428-482 (unfused, host sync per iteration), 40 steps, complex64, same B200"}
         if not args.no_cpu_baseline:
             rate, s_, i_, dt = cpu_oracle_rate(6)
             line["cpu_baseline"] = {"value": rate, "unit": "Msamples/s", "cores": 1, "kind": "port",

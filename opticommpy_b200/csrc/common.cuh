@@ -85,9 +85,15 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // streaming 128-bit accesses (two complex64 per transaction)
 __device__ __forceinline__ float4 ldg4(const float2* p) {
-    return __ldg(reinterpret_cast<const float4*>(p));
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
-__device__ __forceinline__ void stg4(float2* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void stg4(float2* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // Streaming accesses that do not allocate in L1: the field arrays are touched once per kernel, while
 // the small twiddle tables must stay L1-resident (an L1 miss on a table load costs an L2 round trip in

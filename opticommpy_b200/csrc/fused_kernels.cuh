@@ -47,26 +47,6 @@ struct TimeArgs {
     FinalizeExt ext;      // TM_ITER: host mailbox + convergence flag (ext.mail == nullptr: unused)
 };
 
-// phase rotation exp(j ph): short polynomial for the small per-step phases (|ph| < 0.5 rad,
-// truncation error < 1e-9); the rare large phase takes an out-of-line libm call so that the 32
-// unrolled call sites stay small (instruction-cache footprint).
-__device__ __noinline__ float2 phase_rot_slow(float ph) {
-    float s, c;
-    sincosf(ph, &s, &c);
-    return make_float2(c, s);
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ float2 phase_rot(float ph) {
-    float s, c;
-    if (fabsf(ph) >= 0.5f) return phase_rot_slow(ph);
-    {
-        const float x2 = ph * ph;
-        s = ph * fmaf(x2, fmaf(x2, fmaf(x2, -1.9841270e-4f, 8.3333333e-3f), -1.6666667e-1f), 1.0f);
-        c = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
-    }
-    return make_float2(c, s);
-}
-
 // ------------------------------------------------------------------------------------------
 // Time kernel.  64-thread CTA = 64/Q1 row tasks; a task is (time row n2, polarisation) and is owned
 // by Q1 threads (one warp when N1 = 1024).  With NP = 2 the x and y tasks of a row sit in the same

@@ -294,7 +294,11 @@ static int launch_amp(float2* E, int R, int64_t N, double g, double sigma, const
     return 0;
 }
 static int nl_grid(const ocb_ssfm_plan* p, int64_t items) {
-    int g = grid_for(items, 256, 1, 8);
+    // an exact multiple of the SM count (2 CTAs of 256 threads per SM; software-pipelined grid-stride loop)
+    int64_t need = (items + 511) / 512;
+    static const int per_sm = getenv("OCB_NL_CTAS") ? atoi(getenv("OCB_NL_CTAS")) : 2;  // tuning knob (2 measured best)
+    int g = kNumSMs * (per_sm > 0 ? per_sm : 2);
+    if (need < g) g = (int)(need < 1 ? 1 : need);
     return g > p->max_blocks ? p->max_blocks : g;
 }
 static int launch_nl(ocb_ssfm_plan* p, bool first, const float2* Ehd, const float2* Efd, const float2* Ec,
@@ -350,18 +354,23 @@ extern "C" int ocb_manakov_nl_pass(const void* Ehd, const void* Efd, const void*
     cudaStream_t st = (cudaStream_t)stream;
     ocb_ssfm_plan tmp;  // only max_blocks is used
     const bool first = (Efd == nullptr);
-    double* scratch = nullptr;
-    if (!first) {
+    // reduction scratch: allocated once per device and reused (the ticket resets itself after every launch)
+    static thread_local double* scratch = nullptr;
+    static thread_local int scratch_dev = -1;
+    int dev = 0;
+    OCB_CUDA(cudaGetDevice(&dev));
+    const size_t part_bytes = (size_t)tmp.max_blocks * 3 * sizeof(double);
+    if (!first && (scratch == nullptr || scratch_dev != dev)) {
         OCB_REQUIRE(sums3_dev != nullptr, "nl_pass: sums3_dev is NULL");
-        OCB_CUDA(cudaMallocAsync((void**)&scratch, (size_t)tmp.max_blocks * 3 * sizeof(double) + 64, st));
-        OCB_CUDA(cudaMemsetAsync((char*)scratch + (size_t)tmp.max_blocks * 3 * sizeof(double), 0, 64, st));
+        OCB_CUDA(cudaMalloc((void**)&scratch, part_bytes + 64));
+        OCB_CUDA(cudaMemset(scratch, 0, part_bytes + 64));
+        scratch_dev = dev;
     }
+    if (!first) OCB_REQUIRE(sums3_dev != nullptr, "nl_pass: sums3_dev is NULL");
     const double c = (double)direction * hz * (8.0 / 9.0) * gamma * (first ? 1.0 : 0.5);
-    int rc = launch_nl(&tmp, first, (const float2*)Ehd, (const float2*)Efd, (const float2*)Ec, (float*)Pch,
-                       (float2*)out, N, K, (float)c, scratch, (double*)sums3_dev,
-                       scratch ? (unsigned*)((char*)scratch + (size_t)tmp.max_blocks * 3 * sizeof(double)) : nullptr, st);
-    if (scratch) cudaFreeAsync(scratch, st);
-    return rc;
+    return launch_nl(&tmp, first, (const float2*)Ehd, (const float2*)Efd, (const float2*)Ec, (float*)Pch,
+                     (float2*)out, N, K, (float)c, first ? nullptr : scratch, (double*)sums3_dev,
+                     first ? nullptr : (unsigned*)((char*)scratch + part_bytes), st);
 }
 
 extern "C" int ocb_edfa_apply(void* rows_inout, int rows, int64_t N, double gain_lin, double noise_var,

@@ -92,3 +92,33 @@ def test_fused_ssfm_vs_oracle_and_cufft(api):
     out = api.ssfm(x, Bag(Fs=64e9, Ltotal=80, Lspan=80, hz=0.8, alpha=0.0, amp=None, prgsBar=False))
     assert np.sum(np.abs(out) ** 2) == pytest.approx(np.sum(np.abs(x) ** 2), rel=2e-4)
     api.eng.set_default_engine("auto")
+
+
+def test_profiled_and_split_variants_agree(api):
+    """(i) With in-situ profiling on, the loop runs without speculative launches; (ii) OCB_SPLIT=1 selects
+    the pair-split kernels (16 samples per thread) at N = 2^20.  Both must reproduce the default path."""
+    import ctypes as C
+    import os
+    from opticommpy_b200 import _cabi
+    x = field(7, 1 << 20, 2, 6e-3)
+    kw = dict(Fs=512e9, Ltotal=2, Lspan=1, hz=0.25, amp="edfa", seed=3, nlprMethod=False, saveSpanN=[], prgsBar=False)
+    api.eng.set_default_engine("fused")
+    ref = api.manakovSSF(x, Bag(**kw))
+    plan = api.eng.get_plan(1 << 20, 2)
+    _cabi.check(_cabi.lib().ocb_ssfm_plan_profile(plan.handle, 1), "profile on")
+    p = Bag(**kw)
+    out = api.manakovSSF(x, p)
+    prof = (C.c_double * 6)()
+    _cabi.check(_cabi.lib().ocb_ssfm_plan_profile_read(plan.handle, prof), "profile read")
+    _cabi.check(_cabi.lib().ocb_ssfm_plan_profile(plan.handle, 0), "profile off")
+    assert np.array_equal(out, ref)                      # same kernels, same order -> bit-identical
+    assert prof[1] == p._b200_stats["iterations"] and prof[0] > 0
+    os.environ["OCB_SPLIT"] = "1"
+    try:
+        api.eng.clear_plans()
+        out_s = api.manakovSSF(x, Bag(**kw))
+    finally:
+        del os.environ["OCB_SPLIT"]
+        api.eng.clear_plans()
+    assert rel_l2(out_s, ref) < 2e-6
+    api.eng.set_default_engine("auto")
