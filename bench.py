@@ -114,6 +114,16 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(engine):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        return t["k_time_iter_bytes"] if engine == "fused" else t["k_manakov_nl_iter_bytes"]
+    except Exception:
+        return None
+
+
 def cpu_oracle_rate(n_steps, n=N_SAMPLES, seed=0):
     """Time the CPU oracle port on a bounded sample: n_steps fixed steps of the cfg2 fiber at full N."""
     from oracle import fiber_oracle as fo
@@ -376,7 +386,7 @@ def main():
                                                     if plan.engine == "fused" else
                                                     "k_manakov_nl<false,2> (convergence sums + Kerr phase/rotation)"),
                          "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": None,
+                         "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(plan.engine),
                          "launches_timed": int(nl_n), "avg_us": 1e3 * nl_ms / max(nl_n, 1),
                          "bytes_per_launch": bytes_nl},
             "roofline_step": {"model": "64 + 84*I bytes per 2-pol sample-step", "achieved": step_ach, "peak": peak,
