@@ -93,6 +93,11 @@ int ocb_pack_fields(const void* src_dev, int src_dtype, int64_t N, int C, int pa
 int ocb_unpack_fields(const void* rows_dev, int64_t N, int C, int pairs, void* dst_dev,
                       int dst_dtype, void* stream);
 
+/* complex64 <-> complex128 conversion of n samples on the device (host arrays are uploaded raw and
+ * converted here: numpy's complex astype is the slowest part of the host shims otherwise). */
+int ocb_cast_complex(const void* src_dev, int src_dtype, void* dst_dev, int dst_dtype, int64_t n,
+                     void* stream);
+
 /* ---- Manakov SSFM / DBP ---------------------------------------------------------------
  * Replaces optic.models.channels.manakovSSF (channels.py:252-468; direction=+1) and
  * optic.dsp.equalization.manakovDBP (equalization.py:976-1173; direction=-1).          */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ocb_ssfm_plan_profile_read": (_i, [_vp, C.POINTER(C.c_double)]),
     "ocb_pack_fields": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp]),
     "ocb_unpack_fields": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),
+    "ocb_cast_complex": (_i, [_vp, _i, _vp, _i, _i64, _vp]),
     "ocb_manakov_run": (_i, [_vp, _vp, C.POINTER(ManakovParams), _vp, C.POINTER(C.c_int32), _vp,
                              C.POINTER(ManakovStats), _vp]),
     "ocb_manakov_run_host": (_i, [_vp, _vp, _i, _vp, _i, C.POINTER(ManakovParams), _vp,

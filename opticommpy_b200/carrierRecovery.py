@@ -42,12 +42,20 @@ def bps(sigIn, N, constSymb, B, returnIndex=False):
     """
     torch = _cabi.require_cuda()
     lib = _cabi.lib()
-    x = np.ascontiguousarray(np.asarray(sigIn).astype(np.complex128))
+    from . import _engine
+    x = _engine.as_host_complex(np.asarray(sigIn))  # uploaded raw; widened to complex128 on the device
     if x.ndim != 2:
         raise IndexError("bps expects a 2-D (symbols, modes) array")  # sigIn.shape[1], :197
     L, nModes = x.shape
     c = np.ascontiguousarray(np.asarray(constSymb).astype(np.complex128))
-    d_x = torch.from_numpy(x.view(np.float64)).to("cuda")
+    st = _vp(_cabi.stream_ptr(torch))
+    if x.dtype == np.complex128:
+        d_x = torch.from_numpy(x.view(np.float64)).to("cuda")
+    else:
+        d_raw = torch.from_numpy(x.view(np.float32)).to("cuda")
+        d_x = torch.empty((L, nModes, 2), dtype=torch.float64, device="cuda")
+        _cabi.check(lib.ocb_cast_complex(_vp(d_raw.data_ptr()), _cabi.OCB_C64, _vp(d_x.data_ptr()), _cabi.OCB_C128,
+                                         x.size, st), "ocb_cast_complex")
     d_c = torch.from_numpy(c.view(np.float64)).to("cuda")
     d_idx = torch.empty((L, nModes), dtype=torch.int32, device="cuda")
     d_ph = torch.empty((L, nModes), dtype=torch.float64, device="cuda")

@@ -127,11 +127,15 @@ extern "C" int ocb_edc_run(const void* x_rows, void* y_rows, int64_t L, int nMod
 }
 
 // =============================================================================================
-// Adaptive MIMO equalizer: LPS lanes per independent stream (8 for <= 32 taps), each lane owning
-// taps t = l + LPS*j (j < TPL) of all NM*NM sub-filters in registers.  The input samples of a chunk of
-// symbols are staged in shared memory by cp.async (double buffered), so that the per-symbol critical
-// path is: smem window read -> FMAs -> log2(LPS) shuffle stages -> error term -> tap update.
-// Tap layout: H[(m + n*NM), t] = tap t from input mode n to output mode m (equalization.py:467).
+// Adaptive MIMO equalizer.  The tap recurrences of the NM output modes of a stream are independent
+// given the shared input window (every update touches only the rows H[m + n*NM, :] of its own output
+// m), so the unit of work is a TASK = (stream, output mode), owned by LPS lanes (32 for a few streams:
+// one warp per task, the NM tasks of a stream in one CTA; 8 when there are many streams).  Each lane
+// keeps taps t = l + LPS*j (j < TPL) of the NM sub-filters of its output in registers.  The input of a
+// chunk of 128 symbols is staged in shared memory by cp.async (double buffered) and shared by the
+// tasks of the stream; per symbol: smem window read -> FMAs -> log2(LPS) shuffle stages -> error term
+// -> tap update.  Tap layout: H[(m + n*NM), t] = tap t from input mode n to output mode m
+// (equalization.py:467).
 // =============================================================================================
 namespace {
 
@@ -144,23 +148,25 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// CTA = SPB stream slots x NM tasks x LPS lanes ; thread = (slot, m, l)
 template <int NM, int TPL, int LPS, bool WL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* __restrict__ Hg,
           float2* __restrict__ HWg, float2* __restrict__ Y, float* __restrict__ ERR, float2* __restrict__ HIT,
-          int nStreams, int64_t xStride, int64_t refStride, int64_t yStride, int64_t errStride,
+          int nStreams, int SPB, int64_t xStride, int64_t refStride, int64_t yStride, int64_t errStride,
           int64_t errModeStride, int64_t L, int nTaps, int SpS, int alg, float mu,
           const float2* __restrict__ constSymb, int M, const float* __restrict__ radii, int nR, float Rcma) {
-    constexpr int SPW = 32 / LPS;  // streams per warp
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane / LPS, l = lane % LPS;
-    const int slot = warp * SPW + sub;  // stream slot inside the CTA
-    const int stream_raw = blockIdx.x * ((blockDim.x >> 5) * SPW) + slot;
-    const bool live = stream_raw < nStreams;          // dead slots shadow the last stream, never store
+    extern __shared__ __align__(16) float2 smem_eq[];
+    const int tid = threadIdx.x;
+    const int l = tid % LPS;
+    const int m = (tid / LPS) % NM;          // output mode of this task
+    const int slot = tid / (LPS * NM);       // stream slot inside the CTA
+    const int tslot = tid % (LPS * NM);      // thread index inside the stream slot (staging)
+    const int stream_raw = blockIdx.x * SPB + slot;
+    const bool live = stream_raw < nStreams;  // dead slots shadow the last stream, never store
     const int stream = live ? stream_raw : nStreams - 1;
     const int rows_chunk = (kEqChunk - 1) * SpS + nTaps;
-    float2* xbuf = reinterpret_cast<float2*>(smem_raw) + (size_t)slot * 2 * (rows_chunk * NM + kEqChunk * NM);
+    float2* xbuf = smem_eq + (size_t)slot * 2 * (rows_chunk * NM + kEqChunk * NM);
     float2* rbuf = xbuf + 2 * rows_chunk * NM;  // [2][kEqChunk*NM] reference symbols
 
     const float2* x = X + (int64_t)stream * xStride;
@@ -168,20 +174,20 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
     float2* Hs = Hg + (int64_t)stream * NM * NM * nTaps;
     float2* HWs = WL ? HWg + (int64_t)stream * NM * NM * nTaps : nullptr;
     float2* y = Y + (int64_t)stream * yStride;
-    float* err = ERR + (int64_t)stream * errStride;
+    float* err = ERR + (int64_t)stream * errStride + (int64_t)m * errModeStride;
     float2* hit = HIT ? HIT + (int64_t)stream * L * NM * NM * nTaps : nullptr;
 
-    float2 H[NM * NM][TPL], HW[WL ? NM * NM : 1][TPL];
+    float2 H[NM][TPL], HW[WL ? NM : 1][TPL];  // rows m + n*NM, n < NM
 #pragma unroll
-    for (int r = 0; r < NM * NM; ++r)
+    for (int n = 0; n < NM; ++n)
 #pragma unroll
         for (int j = 0; j < TPL; ++j) {
             const int t = l + LPS * j;
-            H[r][j] = t < nTaps ? Hs[r * nTaps + t] : make_float2(0.f, 0.f);
-            if (WL) HW[r][j] = t < nTaps ? HWs[r * nTaps + t] : make_float2(0.f, 0.f);
+            H[n][j] = t < nTaps ? Hs[(m + n * NM) * nTaps + t] : make_float2(0.f, 0.f);
+            if (WL) HW[n][j] = t < nTaps ? HWs[(m + n * NM) * nTaps + t] : make_float2(0.f, 0.f);
         }
 
-    // stage chunk k (symbols [k*CH, min(L, (k+1)*CH))) into buffer k&1
+    // stage chunk k (symbols [k*CH, min(L, (k+1)*CH))) into buffer k&1; all NM*LPS threads of the slot copy
     auto stage = [&](int64_t k) {
         const int64_t s0 = k * kEqChunk;
         if (s0 >= L) return;
@@ -189,17 +195,15 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
         const int rows = (nsym - 1) * SpS + nTaps;
         float2* dst = xbuf + (k & 1) * rows_chunk * NM;
         const float2* src = x + s0 * SpS * NM;
-        for (int i = l; i < rows * NM; i += LPS) cp_async8(dst + i, src + i);
+        for (int i = tslot; i < rows * NM; i += LPS * NM) cp_async8(dst + i, src + i);
         if (ref) {
             float2* rd = rbuf + (k & 1) * kEqChunk * NM;
             const float2* rs = ref + s0 * NM;
-            for (int i = l; i < nsym * NM; i += LPS) cp_async8(rd + i, rs + i);
+            for (int i = tslot; i < nsym * NM; i += LPS * NM) cp_async8(rd + i, rs + i);
         }
     };
 
-    float prev_err[NM];
-#pragma unroll
-    for (int m = 0; m < NM; ++m) prev_err[m] = 0.f;
+    float prev_err = 0.f;
     constexpr int kMaxR = 8;  // radii kept in registers (16/64-QAM have 3/9 rings; more fall back to memory)
     float rad[kMaxR];
 #pragma unroll
@@ -210,8 +214,8 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
     const int64_t nchunks = (L + kEqChunk - 1) / kEqChunk;
     for (int64_t k = 0; k < nchunks; ++k) {
         cp_async_wait_all();
-        __syncwarp();
-        stage(k + 1);  // lands while this chunk is processed
+        __syncthreads();  // chunk k landed for every task of the CTA; chunk k-1 fully consumed
+        stage(k + 1);     // lands while this chunk is processed
         cp_async_commit();
         const float2* xb = xbuf + (k & 1) * rows_chunk * NM;
         const float2* rb = rbuf + (k & 1) * kEqChunk * NM;
@@ -228,25 +232,20 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
 #pragma unroll
                 for (int n = 0; n < NM; ++n) w[n][j] = (t < nTaps) ? p[n] : make_float2(0.f, 0.f);
             }
-            // ---- filter: out[m] = sum_n H[m + n NM, :] . x_n[window]   (equalization.py:464-471)
-            float2 o[NM];
+            // ---- filter: out_m = sum_n H[m + n NM, :] . x_n[window]   (equalization.py:464-471)
+            float2 o = make_float2(0.f, 0.f);
             float nrm[NM];
 #pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                float2 acc = make_float2(0.f, 0.f);
+            for (int n = 0; n < NM; ++n)
 #pragma unroll
-                for (int n = 0; n < NM; ++n)
-#pragma unroll
-                    for (int j = 0; j < TPL; ++j) {
-                        float2 pr = cmul(H[m + n * NM][j], w[n][j]);
-                        acc.x += pr.x; acc.y += pr.y;
-                        if (WL) {
-                            float2 qq = cmul_conj(HW[m + n * NM][j], w[n][j]);  // H_ . conj(x)
-                            acc.x += qq.x; acc.y += qq.y;
-                        }
+                for (int j = 0; j < TPL; ++j) {
+                    float2 pr = cmul(H[n][j], w[n][j]);
+                    o.x += pr.x; o.y += pr.y;
+                    if (WL) {
+                        float2 qq = cmul_conj(HW[n][j], w[n][j]);  // H_ . conj(x)
+                        o.x += qq.x; o.y += qq.y;
                     }
-                o[m] = acc;
-            }
+                }
             if (alg == OCB_ALG_NLMS) {
 #pragma unroll
                 for (int n = 0; n < NM; ++n) {
@@ -258,117 +257,98 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
             }
 #pragma unroll
             for (int off = LPS / 2; off > 0; off >>= 1) {
-#pragma unroll
-                for (int m = 0; m < NM; ++m) {
-                    o[m].x += __shfl_xor_sync(0xffffffffu, o[m].x, off);
-                    o[m].y += __shfl_xor_sync(0xffffffffu, o[m].y, off);
-                }
+                o.x += __shfl_xor_sync(0xffffffffu, o.x, off);
+                o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
                 if (alg == OCB_ALG_NLMS) {
 #pragma unroll
                     for (int n = 0; n < NM; ++n) nrm[n] += __shfl_xor_sync(0xffffffffu, nrm[n], off);
                 }
             }
-            if (live && l < NM) {
-                float2 sel = o[0];
-#pragma unroll
-                for (int m = 1; m < NM; ++m) if (l == m) sel = o[m];
-                y[ind * NM + l] = sel;  // equalization.py:473
-            }
+            if (live && l == 0) y[ind * NM + m] = o;  // equalization.py:473
 
-            // ---- error term g_m and squared error, per algorithm
-            float2 g[NM];
-            float esq[NM];
+            // ---- error term g and squared error, per algorithm
+            float2 g;
+            float esq;
+            const float a2 = cabs2(o);
+            if (alg == OCB_ALG_CMA) {  // :826-829
+                float e = Rcma - a2;
+                g = make_float2(e * o.x, e * o.y);
+                esq = e * e;
+            } else if (alg == OCB_ALG_RDE || alg == OCB_ALG_DARDE) {  // :887-894, :953-959
+                float Rd;
+                if (alg == OCB_ALG_RDE) {
+                    float r = sqrtf(a2);
+                    float best = fabsf(rad[0] - r);
+                    Rd = rad[0];
 #pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                const float a2 = cabs2(o[m]);
-                if (alg == OCB_ALG_CMA) {  // :826-829
-                    float e = Rcma - a2;
-                    g[m] = make_float2(e * o[m].x, e * o[m].y);
-                    esq[m] = e * e;
-                } else if (alg == OCB_ALG_RDE || alg == OCB_ALG_DARDE) {  // :887-894, :953-959
-                    float Rd;
-                    if (alg == OCB_ALG_RDE) {
-                        float r = sqrtf(a2);
-                        float best = fabsf(rad[0] - r);
-                        Rd = rad[0];
-#pragma unroll
-                        for (int i = 1; i < kMaxR; ++i) {
-                            float dd = fabsf(rad[i] - r);
-                            if (dd < best) { best = dd; Rd = rad[i]; }
-                        }
-                        for (int i = kMaxR; i < nR; ++i) {
-                            float dd = fabsf(radii[i] - r);
-                            if (dd < best) { best = dd; Rd = radii[i]; }
-                        }
-                    } else {
-                        Rd = sqrtf(cabs2(rb[s * NM + m]));
+                    for (int i = 1; i < kMaxR; ++i) {
+                        float dd = fabsf(rad[i] - r);
+                        if (dd < best) { best = dd; Rd = rad[i]; }
                     }
-                    float e = Rd * Rd - a2;
-                    g[m] = make_float2(e * o[m].x, e * o[m].y);
-                    esq[m] = e * e;
-                } else if (alg == OCB_ALG_NLMS) {  // :556
-                    float2 sr = rb[s * NM + m];
-                    g[m] = make_float2(sr.x - o[m].x, sr.y - o[m].y);
-                    esq[m] = cabs2(g[m]);
-                } else if (alg == OCB_ALG_DDLMS) {  // :688-691  nearest constellation point, first index on ties
-                    float best = 3.4e38f;
-                    int bi = 0x7fffffff;
-                    for (int c = l; c < M; c += LPS) {
-                        float2 sc = __ldg(constSymb + c);
-                        float dd = cabs2(make_float2(o[m].x - sc.x, o[m].y - sc.y));
-                        if (dd < best) { best = dd; bi = c; }
+                    for (int i = kMaxR; i < nR; ++i) {
+                        float dd = fabsf(radii[i] - r);
+                        if (dd < best) { best = dd; Rd = radii[i]; }
                     }
-#pragma unroll
-                    for (int off = LPS / 2; off > 0; off >>= 1) {
-                        float ob = __shfl_xor_sync(0xffffffffu, best, off);
-                        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                    }
-                    float2 sc = __ldg(constSymb + bi);
-                    g[m] = make_float2(sc.x - o[m].x, sc.y - o[m].y);
-                    esq[m] = cabs2(g[m]);
-                } else {  // static: no update (:505-506)
-                    g[m] = make_float2(0.f, 0.f);
-                    esq[m] = prev_err[m];
+                } else {
+                    Rd = sqrtf(cabs2(rb[s * NM + m]));
                 }
-                prev_err[m] = esq[m];
-            }
-            if (live && l < NM) {
-                float sel = esq[0];
+                float e = Rd * Rd - a2;
+                g = make_float2(e * o.x, e * o.y);
+                esq = e * e;
+            } else if (alg == OCB_ALG_NLMS) {  // :556
+                float2 sr = rb[s * NM + m];
+                g = make_float2(sr.x - o.x, sr.y - o.y);
+                esq = cabs2(g);
+            } else if (alg == OCB_ALG_DDLMS) {  // :688-691  nearest constellation point, first index on ties
+                float best = 3.4e38f;
+                int bi = 0x7fffffff;
+                for (int c = l; c < M; c += LPS) {
+                    float2 sc = __ldg(constSymb + c);
+                    float dd = cabs2(make_float2(o.x - sc.x, o.y - sc.y));
+                    if (dd < best) { best = dd; bi = c; }
+                }
 #pragma unroll
-                for (int m = 1; m < NM; ++m) if (l == m) sel = esq[m];
-                err[(int64_t)l * errModeStride + ind] = sel;
+                for (int off = LPS / 2; off > 0; off >>= 1) {
+                    float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                float2 sc = __ldg(constSymb + bi);
+                g = make_float2(sc.x - o.x, sc.y - o.y);
+                esq = cabs2(g);
+            } else {  // static: no update (:505-506)
+                g = make_float2(0.f, 0.f);
+                esq = prev_err;
             }
+            prev_err = esq;
+            if (live && l == 0) err[ind] = esq;
 
-            // ---- tap update: H[m + n NM, :] += mu g_m conj(x_n)   (:838-840 and siblings)
+            // ---- tap update: H[m + n NM, :] += mu g conj(x_n)   (:838-840 and siblings)
             if (alg != OCB_ALG_STATIC) {
+                const float2 wg = make_float2(mu * g.x, mu * g.y);
 #pragma unroll
-                for (int m = 0; m < NM; ++m) {
-                    const float2 wg = make_float2(mu * g[m].x, mu * g[m].y);
+                for (int n = 0; n < NM; ++n) {
+                    const float inv = (alg == OCB_ALG_NLMS) ? 1.0f / nrm[n] : 1.0f;
 #pragma unroll
-                    for (int n = 0; n < NM; ++n) {
-                        const float inv = (alg == OCB_ALG_NLMS) ? 1.0f / nrm[n] : 1.0f;
-#pragma unroll
-                        for (int j = 0; j < TPL; ++j) {
-                            float2 xin = w[n][j];
-                            if (alg == OCB_ALG_NLMS) { xin.x *= inv; xin.y *= inv; }  // :563
-                            float2 u = cmul_conj(wg, xin);
-                            H[m + n * NM][j].x += u.x; H[m + n * NM][j].y += u.y;
-                            if (WL) {
-                                float2 vv = cmul(wg, xin);
-                                HW[m + n * NM][j].x += vv.x; HW[m + n * NM][j].y += vv.y;
-                            }
+                    for (int j = 0; j < TPL; ++j) {
+                        float2 xin = w[n][j];
+                        if (alg == OCB_ALG_NLMS) { xin.x *= inv; xin.y *= inv; }  // :563
+                        float2 u = cmul_conj(wg, xin);
+                        H[n][j].x += u.x; H[n][j].y += u.y;
+                        if (WL) {
+                            float2 vv = cmul(wg, xin);
+                            HW[n][j].x += vv.x; HW[n][j].y += vv.y;
                         }
                     }
                 }
             }
             if (hit && live) {  // storeCoeff (:511-512): Hiter[:, :, ind] = H, stored as (L, NM^2, nTaps)
 #pragma unroll
-                for (int r = 0; r < NM * NM; ++r)
+                for (int n = 0; n < NM; ++n)
 #pragma unroll
                     for (int j = 0; j < TPL; ++j) {
                         const int t = l + LPS * j;
-                        if (t < nTaps) hit[(ind * NM * NM + r) * nTaps + t] = H[r][j];
+                        if (t < nTaps) hit[(ind * NM * NM + m + n * NM) * nTaps + t] = H[n][j];
                     }
             }
         }
@@ -377,13 +357,13 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
 
     if (live) {
 #pragma unroll
-        for (int r = 0; r < NM * NM; ++r)
+        for (int n = 0; n < NM; ++n)
 #pragma unroll
             for (int j = 0; j < TPL; ++j) {
                 const int t = l + LPS * j;
                 if (t < nTaps) {
-                    Hs[r * nTaps + t] = H[r][j];
-                    if (WL) HWs[r * nTaps + t] = HW[r][j];
+                    Hs[(m + n * NM) * nTaps + t] = H[n][j];
+                    if (WL) HWs[(m + n * NM) * nTaps + t] = HW[n][j];
                 }
             }
     }
@@ -394,17 +374,19 @@ int launch_mimo(bool wl, cudaStream_t st, const float2* X, const float2* REF, fl
                 float2* HW, float2* Y, float* ERR, float2* HIT, int nStreams, int64_t xs, int64_t rs, int64_t ys,
                 int64_t es, int64_t ems, int64_t L, int nTaps,
                 int SpS, int alg, float mu, const float2* cs, int M, const float* radii, int nR, float Rcma) {
-    constexpr int SPB = 32 / LPS;  // streams per one-warp CTA (keeps the staged chunks of a CTA small)
-    const int grid = (nStreams + SPB - 1) / SPB;
+    // stream slots per CTA: one in latency mode (CTA = NM warps), up to 128 threads' worth otherwise
+    const int spb = (LPS == 32) ? 1 : (128 / (LPS * NM) > 0 ? 128 / (LPS * NM) : 1);
+    const int grid = (nStreams + spb - 1) / spb;
+    const int block = spb * NM * LPS;
     const int rows_chunk = (kEqChunk - 1) * SpS + nTaps;
-    const size_t smem = (size_t)SPB * 2 * ((size_t)rows_chunk * NM + kEqChunk * NM) * sizeof(float2);
+    const size_t smem = (size_t)spb * 2 * ((size_t)rows_chunk * NM + kEqChunk * NM) * sizeof(float2);
     OCB_REQUIRE(smem <= 200 * 1024, "mimo_eq_run: SpS/nTaps too large for the staged input chunk");
     if (wl) {
         OCB_CUDA(cudaFuncSetAttribute(k_mimo_eq<NM, TPL, LPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OCB_LAUNCH((k_mimo_eq<NM, TPL, LPS, true>), grid, 32, smem, st, X, REF, H, HW, Y, ERR, HIT, nStreams, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
+        OCB_LAUNCH((k_mimo_eq<NM, TPL, LPS, true>), grid, block, smem, st, X, REF, H, HW, Y, ERR, HIT, nStreams, spb, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
     } else {
         OCB_CUDA(cudaFuncSetAttribute(k_mimo_eq<NM, TPL, LPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OCB_LAUNCH((k_mimo_eq<NM, TPL, LPS, false>), grid, 32, smem, st, X, REF, H, HW, Y, ERR, HIT, nStreams, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
+        OCB_LAUNCH((k_mimo_eq<NM, TPL, LPS, false>), grid, block, smem, st, X, REF, H, HW, Y, ERR, HIT, nStreams, spb, xs, rs, ys, es, ems, L, nTaps, SpS, alg, mu, cs, M, radii, nR, Rcma);
     }
     return 0;
 }

@@ -276,6 +276,28 @@ extern "C" int ocb_unpack_fields(const void* rows, int64_t N, int C, int pairs, 
     return 0;
 }
 
+// dtype conversion without reordering (complex64 <-> complex128), e.g. host arrays uploaded raw
+template <typename TI, typename TO>
+__global__ void k_cast_complex(const TI* __restrict__ src, TO* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        TI v = src[i];
+        TO o; o.x = v.x; o.y = v.y;
+        dst[i] = o;
+    }
+}
+extern "C" int ocb_cast_complex(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+    OCB_REQUIRE(src && dst && n >= 0, "cast_complex: bad argument");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(n, 256, 2);
+    if (src_dtype == OCB_C128 && dst_dtype == OCB_C64) OCB_LAUNCH((k_cast_complex<double2, float2>), g, 256, 0, st, (const double2*)src, (float2*)dst, n);
+    else if (src_dtype == OCB_C64 && dst_dtype == OCB_C128) OCB_LAUNCH((k_cast_complex<float2, double2>), g, 256, 0, st, (const float2*)src, (double2*)dst, n);
+    else if (src_dtype == OCB_C64 && dst_dtype == OCB_C64) OCB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    else if (src_dtype == OCB_C128 && dst_dtype == OCB_C128) OCB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
+    else return fail("cast_complex: unknown dtype", __FILE__, __LINE__);
+    return 0;
+}
+
 // ---- small launch helpers --------------------------------------------------------------------
 static int launch_table(ocb_ssfm_plan* p, float2* T, double a, double b, double Fs, double h,
                         double scale, cudaStream_t st) {

@@ -135,7 +135,7 @@ def _parse_equalizer_args(sigIn, param, symbRef):
 
     sigIn = np.asarray(sigIn)
     if not len(symbRef):
-        symbRef = sigIn.copy()
+        symbRef = sigIn  # the reference copies; nothing here mutates either array
     symbRef = np.asarray(symbRef)
     try:
         if sigIn.shape[1] > sigIn.shape[0]:
@@ -151,17 +151,19 @@ def _parse_equalizer_args(sigIn, param, symbRef):
         symbRef = symbRef.reshape(len(symbRef), 1)
     s.nModes = int(sigIn.shape[1])
 
-    s.symbRef = np.ascontiguousarray(symbRef.astype(np.complex64))
-    sig = sigIn.astype(np.complex64)
+    # The casts to prec=complex64 (:222-223) and the zero padding of floor(nTaps/2) rows (:227-231) are
+    # done on the device: the raw arrays are uploaded as they are (numpy's complex astype is slow).
+    needs_ref = any(a in ("nlms", "da-rde") for a in (s.alg if isinstance(s.alg, list) else []))
+    s.symbRef = _engine.as_host_complex(symbRef) if needs_ref else None
+    s.sig = _engine.as_host_complex(sigIn)
     s.mu = np.atleast_1d(np.array(mu).astype(np.float32))
 
     Lpad = int(np.floor(s.nTaps / 2))
-    zeroPad = np.zeros((Lpad, s.nModes), dtype=np.complex64)
-    s.sigPad = np.ascontiguousarray(np.concatenate((zeroPad, sig, zeroPad)))  # equalization.py:227-231
     s.Lpad = Lpad
+    s.nPad = s.sig.shape[0] + 2 * Lpad
 
     s.constSymb = normalizedConstellation(M, constType, shapingFactor, np.complex64)  # :234-241
-    s.totalNumSymb = int(np.fix((len(s.sigPad) - s.nTaps) / s.SpS + 1))  # :243
+    s.totalNumSymb = int(np.fix((s.nPad - s.nTaps) / s.SpS + 1))  # :243
 
     if isinstance(L, np.ndarray):
         L = L.tolist()
@@ -207,16 +209,29 @@ def _run_equalizer_batch(setups):
     st = _vp(_cabi.stream_ptr(torch))
     s0 = setups[0]
     nS, nM, nT, SpS = len(setups), s0.nModes, s0.nTaps, s0.SpS
-    nSamp = s0.sigPad.shape[0]
+    nSamp = s0.nPad
     for s in setups[1:]:
-        if (s.nModes, s.nTaps, s.SpS, s.sigPad.shape[0], s.alg, s.L, s.numIter, s.runWL) != \
+        if (s.nModes, s.nTaps, s.SpS, s.nPad, s.alg, s.L, s.numIter, s.runWL) != \
            (nM, nT, SpS, nSamp, s0.alg, s0.L, s0.numIter, s0.runWL) or not np.array_equal(s.mu, s0.mu):
             raise ValueError("all streams of a batch must share geometry, stages and step sizes")
     total = s0.totalNumSymb
-    Lref = min(s.symbRef.shape[0] for s in setups)
+    has_ref = all(s.symbRef is not None for s in setups)
+    Lref = min(s.symbRef.shape[0] for s in setups) if has_ref else 0
 
-    d_x = _to_device(torch, np.stack([s.sigPad for s in setups]).view(np.float32))
-    d_ref = _to_device(torch, np.stack([s.symbRef[:Lref] for s in setups]).view(np.float32))
+    def upload_c64(arr, dst_view):
+        """raw H2D copy of a complex64/128 host array, converted to complex64 into dst_view (device)"""
+        raw = torch.from_numpy(arr.view(np.float32 if arr.dtype == np.complex64 else np.float64)).to("cuda")
+        _cabi.check(lib.ocb_cast_complex(_ptr(raw), _engine.dtype_tag(arr.dtype), _vp(dst_view.data_ptr()),
+                                         _cabi.OCB_C64, arr.size, st), "ocb_cast_complex")
+        return raw  # keep alive until the stream has consumed it
+
+    d_x = torch.zeros((nS, nSamp, nM, 2), dtype=torch.float32, device="cuda")  # zero rows = the padding
+    keep = [upload_c64(s.sig, d_x[i, s.Lpad:s.Lpad + s.sig.shape[0]]) for i, s in enumerate(setups)]
+    if has_ref:
+        d_ref = torch.empty((nS, Lref, nM, 2), dtype=torch.float32, device="cuda")
+        keep += [upload_c64(np.ascontiguousarray(s.symbRef[:Lref]), d_ref[i]) for i, s in enumerate(setups)]
+    else:
+        d_ref = None
     d_H = _to_device(torch, np.stack([s.H for s in setups]).view(np.float32))
     d_Hw = _to_device(torch, np.stack([s.H_ for s in setups]).view(np.float32)) if s0.runWL else None
     d_c = _to_device(torch, s0.constSymb.view(np.float32))
@@ -241,7 +256,7 @@ def _run_equalizer_batch(setups):
                 d_hit = torch.empty((nS, Ls, nM * nM, nT, 2), dtype=torch.float32, device="cuda")
             _cabi.check(
                 lib.ocb_mimo_eq_run(
-                    _ptr(d_x, nStart * SpS * nM * 8), _ptr(d_ref, nStart * nM * 8), _ptr(d_H),
+                    _ptr(d_x, nStart * SpS * nM * 8), _ptr(d_ref, nStart * nM * 8) if d_ref is not None else None, _ptr(d_H),
                     _ptr(d_Hw) if d_Hw is not None else None, _ptr(d_y, nStart * nM * 8), _ptr(d_e, nStart * 4),
                     _ptr(d_hit) if d_hit is not None else None,
                     nS, nSamp - nStart * SpS, nSamp * nM, Lref * nM, total * nM, nM * total, total,

@@ -80,7 +80,7 @@ def test_equalizer_argument_parsing(golden):
     from opticommpy_b200.equalization import _parse_equalizer_args
     s = _parse_equalizer_args(golden["eq_in"].T, Bag(nTaps=15, SpS=2, M=16, alg=["cma", "rde"], mu=[5e-3, 2e-3],
                                                      L=[1000, 2000]), None)
-    assert s.nModes == 2 and s.sigPad.shape == (6000 + 14, 2) and s.totalNumSymb == 3000
+    assert s.nModes == 2 and s.nPad == 6000 + 14 and s.totalNumSymb == 3000 and s.symbRef is None
     assert s.H[0, 7] == 1 and s.H[3, 7] == 1 and np.count_nonzero(s.H) == 2
     assert s.mu.dtype == np.float32 and len(s.Rrde) == 3
     assert s.Rcma == pytest.approx(1.32, abs=1e-6)

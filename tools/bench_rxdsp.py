@@ -85,6 +85,16 @@ def main():
     tc_eq = time.perf_counter() - t0
     t0 = time.perf_counter(); ro.cpr_bps(y2c, grayMapping(16, "qam"), N=25, B=64, runFOE=False); tc_cpr = time.perf_counter() - t0
     ms = lambda n, t: n / t / 1e6
+    # many independent streams (WDM channels x Monte-Carlo realisations): the regime the per-stream warp
+    # design is for.  1184 streams (8 per SM) x 2^13 symbols, device-resident timing of the kernels only.
+    from opticommpy_b200.equalization import mimoAdaptEqualizerBatch
+    nb, lb = 1184, 1 << 13
+    xb = [x[i * 64:i * 64 + 2 * lb] for i in range(nb)]
+    pb = Bag(nTaps=31, SpS=2, M=16, constType="qam", alg=["cma", "rde"], mu=[5e-3, 2e-4],
+             L=[lb // 4, lb - lb // 4], prgsBar=False)
+    mimoAdaptEqualizerBatch(xb[:8], pb)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); yb = mimoAdaptEqualizerBatch(xb, pb); torch.cuda.synchronize(); t_batch = time.perf_counter() - t0
     print(json.dumps({
         "workload": f"cfg3: edc(800 km, 448 taps) + 2x2 mimoAdaptEqualizer(CMA->RDE, 31 taps) + cpr/bps(B=64, N=25) on 2^{a.nsym_log2 + 1} samples x 2 pol",
         "gpu_input_Msamples_per_s": {"edc": ms(2 * nsym, t_edc), "mimoAdaptEqualizer": ms(2 * nsym, t_eq), "cpr_bps": ms(2 * nsym, t_cpr),
@@ -93,6 +103,9 @@ def main():
         "cpu_oracle_input_Msamples_per_s": {"edc": ms(2 * n_cpu, tc_edc), "mimoAdaptEqualizer": ms(2 * n_cpu, tc_eq),
                                             "cpr_bps": ms(2 * n_cpu, tc_cpr), "chain": ms(2 * n_cpu, tc_edc + tc_eq + tc_cpr),
                                             "sample": f"2^{a.cpu_nsym_log2} symbols, 1 core"},
+        "equalizer_batch": {"streams": nb, "symbols_per_stream": lb, "seconds_incl_host": t_batch,
+                            "aggregate_Msym_per_s": nb * lb / t_batch / 1e6,
+                            "aggregate_input_Msamples_per_s": 2 * nb * lb / t_batch / 1e6},
         "api": "public drop-in calls, numpy in / numpy out (H2D + D2H inside)",
     }))
 
