@@ -108,6 +108,13 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     asm("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+// Same load, but ordered against the (volatile) st_stream stores: for buffers that a kernel updates in
+// place (volatile asm statements keep their program order).
+__device__ __forceinline__ float2 ld_stream_ordered(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_stream(float2* p, float2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }

@@ -111,7 +111,9 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
     const size_t field_bytes = (size_t)R * N * sizeof(float2);
     if (fused_init_tables(p, st)) return 1;
     const bool split = p->split;
-    float2* bufs[3] = {p->A, p->B, p->Cb};
+    // One field buffer: k_time<TM_ITER> replaces the previous iterate by the new one in place, which keeps
+    // the per-iteration working set (W, E_c, E_hd, P_ch, operator table = 60 MB at N = 2^20) inside L2.
+    float2* bufs[3] = {p->A, p->A, p->A};
     float2* Wb = p->G;
     float2* LP = p->T1;
     int cur = 0;

@@ -142,16 +142,24 @@ k_time(const TimeArgs A) {
                 pown[Q1 * a + t] = cabs2(ld_stream(ech + Q1 * a + t));
             }
         } else {
-            // v = E_fd: convergence sums against the previous iterate, store as the new iterate
+            // v = E_fd: convergence sums against the previous iterate, store as the new iterate.  aux0 and
+            // aux1 may be the SAME buffer (in-place update keeps the working set L2-sized): every thread
+            // reads its own samples before it overwrites them; two batches of 16 keep the loads in flight.
             const float2* ec = A.aux0 + base;
             float2* ec_new = A.aux1 + base;
 #pragma unroll
-            for (int a = 0; a < 32; ++a) {
-                const float2 e = ld_stream(ec + Q1 * a + t);
-                s_num += cabs2(make_float2(v[a].x - e.x, v[a].y - e.y));  // channels.py:517
-                s_den += cabs2(e);
-                st_stream(ec_new + Q1 * a + t, v[a]);
-                pown[Q1 * a + t] = cabs2(v[a]);
+            for (int hb = 0; hb < 2; ++hb) {
+                float2 e[16];
+#pragma unroll
+                for (int a = 0; a < 16; ++a) e[a] = ld_stream_ordered(ec + Q1 * (16 * hb + a) + t);
+#pragma unroll
+                for (int a = 0; a < 16; ++a) {
+                    const int aa = 16 * hb + a;
+                    s_num += cabs2(make_float2(v[aa].x - e[a].x, v[aa].y - e[a].y));  // channels.py:517
+                    s_den += cabs2(e[a]);
+                    st_stream(ec_new + Q1 * aa + t, v[aa]);
+                    pown[Q1 * aa + t] = cabs2(v[aa]);
+                }
             }
         }
         __syncthreads();
