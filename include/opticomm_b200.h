@@ -217,6 +217,18 @@ int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hwl, void* y,
 int ocb_bps_run(const void* x, int64_t L, int nModes, const void* constSymb, int M, int B, int Nhalf,
                 void* idx_out, void* phase_out, void* stream);
 
+/* ---- carrier phase recovery wrapper -----------------------------------------------------------------
+ * Replaces optic.dsp.carrierRecovery.cpr with alg='bps' (carrierRecovery.py:110-169) in one call, all on
+ * the device and in float64 like the reference: optional fourthPowerFOE (:333-371) + pnorm, bps (:138),
+ * unwrap(4*phase)/4 (:154), pnorm(x * exp(j*phase)) (:162).
+ *   x_dev : (L, nModes) complex64/128 ; constSymb : (M) complex128 (power-normalised constellation)
+ *   y_out : (L, nModes) complex128 ; phase_out : (L, nModes) float64 unwrapped phases
+ *   fo_host : nModes estimated frequency offsets [Hz] (host array, may be NULL)                     */
+int64_t ocb_cpr_workspace_bytes(int64_t L, int nModes);
+int ocb_cpr_bps_run(const void* x_dev, int x_dtype, int64_t L, int nModes, const void* constSymb, int M,
+                    int B, int Nhalf, int runFOE, double Fs, int foeM, void* y_out, void* phase_out,
+                    double* fo_host, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,9 @@ SIGNATURES = {
     "ocb_mimo_eq_run": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                              _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _f, _i, _vp]),
     "ocb_bps_run": (_i, [_vp, _i64, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ocb_cpr_workspace_bytes": (_i64, [_i64, _i]),
+    "ocb_cpr_bps_run": (_i, [_vp, _i, _i64, _i, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp, C.POINTER(C.c_double), _vp,
+                             _i64, _vp]),
 }
 
 

@@ -1,9 +1,10 @@
 """Drop-in mirrors of ``optic.dsp.carrierRecovery.bps`` and the ``cpr`` wrapper around it.
 
 ``bps`` (carrierRecovery.py:172-223) runs on the GPU through ``ocb_bps_run`` in float64, like the
-reference.  ``cpr`` (carrierRecovery.py:37-169) keeps the reference's parameter names, defaults
-and post-processing (4th-power FOE, ``unwrap(4φ)/4``, power normalisation); only ``alg='bps'``
-(and its alias ``'bpsGPU'``, the reference's own GPU selector) is part of this hot path.
+reference.  ``cpr`` (carrierRecovery.py:37-169) keeps the reference's parameter names and defaults and
+runs the whole wrapper — 4th-power FOE, power normalisation, bps, ``unwrap(4φ)/4``, de-rotation — in one
+device call (``ocb_cpr_bps_run``); only ``alg='bps'`` (and its alias ``'bpsGPU'``, the reference's own GPU
+selector) is part of this hot path.
 """
 from __future__ import annotations
 
@@ -118,29 +119,47 @@ def cpr(sigIn, param=None, symbTx=None):
     px = px / np.sum(px)
     constSymb /= np.sqrt(np.sum(np.abs(constSymb) ** 2 * px))
 
-    if runFOE:  # :124-131
-        logg.info("Running frequency offset compensation...")
-        sigIn, fo = fourthPowerFOE(sigIn, 1 / Ts, M if constType in ["psk", "apsk"] else 4)
-        sigIn = _pnorm(sigIn)
-        logg.info(f"Estimated frequency offset (MHz): {np.round(fo / 1e6, 3)}")
-
-    if alg in ("bps", "bpsGPU"):
-        logg.info("Running BPS carrier phase recovery...")
-        phaseEst = bps(sigIn, N // 2, constSymb, B)  # :138
-    elif alg in ("ddpll", "viterbi"):
+    if alg in ("ddpll", "viterbi"):
         raise NotImplementedError(f"cpr alg '{alg}' is outside the B200 hot path (SURVEY.md §2 row 3)")
-    else:
+    if alg not in ("bps", "bpsGPU"):
         logg.error("CPR algorithm incorrectly specified.")
         raise NameError("name 'phaseEst' is not defined")  # the reference falls through to :154
 
-    phaseEst = np.unwrap(4 * phaseEst, axis=0) / 4  # :154
+    # FOE + pnorm (:124-131), bps (:138), unwrap(4φ)/4 (:154) and pnorm(x·e^{jφ}) (:162) in one device call
+    torch = _cabi.require_cuda()
+    lib = _cabi.lib()
+    from . import _engine
+    x = _engine.as_host_complex(sigIn)
+    L, nModes = x.shape
+    c128 = np.ascontiguousarray(constSymb.astype(np.complex128))
+    st = _vp(_cabi.stream_ptr(torch))
+    d_x = torch.from_numpy(x.view(np.float32 if x.dtype == np.complex64 else np.float64)).to("cuda")
+    d_c = torch.from_numpy(c128.view(np.float64)).to("cuda")
+    d_y = torch.empty((L, nModes, 2), dtype=torch.float64, device="cuda")
+    d_ph = torch.empty((L, nModes), dtype=torch.float64, device="cuda")
+    ws_bytes = int(lib.ocb_cpr_workspace_bytes(L, nModes))
+    d_ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (d_ws.data_ptr() + 255) // 256 * 256
+    fo = (C.c_double * nModes)()
+    foeM = M if constType in ["psk", "apsk"] else 4
+    if runFOE:
+        logg.info("Running frequency offset compensation...")
+    logg.info("Running BPS carrier phase recovery...")
+    _cabi.check(
+        lib.ocb_cpr_bps_run(_vp(d_x.data_ptr()), _engine.dtype_tag(x.dtype), L, nModes, _vp(d_c.data_ptr()), len(c128),
+                            int(B), int(N // 2), int(bool(runFOE)), float(1 / Ts), int(foeM), _vp(d_y.data_ptr()),
+                            _vp(d_ph.data_ptr()), fo, _vp(ws_ptr), ws_bytes, st),
+        "ocb_cpr_bps_run",
+    )
+    if runFOE:
+        logg.info(f"Estimated frequency offset (MHz): {np.round(np.array(fo[:]) / 1e6, 3)}")
+    sigOut = d_y.cpu().numpy().view(np.complex128).reshape(L, nModes)
+    phaseEst = d_ph.cpu().numpy()
 
     discard = phaseEst.shape[0] // 4
-    if discard > 0:
+    if discard > 0 and logg.getLogger().isEnabledFor(logg.INFO):
         sigmaPhase = np.mean(np.var(np.diff(phaseEst[discard:-discard, :], axis=0), axis=0))
         logg.info(f"Estimated linewidth: {sigmaPhase / (2 * np.pi * Ts) / 1e3:.3f} kHz")
-
-    sigOut = _pnorm(sigIn * np.exp(1j * phaseEst))  # :162
 
     if input1D:
         sigOut = sigOut.flatten()

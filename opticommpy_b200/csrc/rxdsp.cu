@@ -5,6 +5,8 @@
 //   bps                    : optic/dsp/carrierRecovery.py:172-223
 #include <math.h>
 
+#include <type_traits>
+
 #include "../../include/opticomm_b200.h"
 #include "common.cuh"
 
@@ -209,6 +211,10 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
 #pragma unroll
     for (int i = 0; i < kMaxR; ++i) rad[i] = (radii && i < nR) ? radii[i] : 3.0e38f;
 
+    // The symbol loop is instantiated once per algorithm (compile-time ALG) so that no algorithm dispatch,
+    // constant-bank reload or dead select chain sits on the per-symbol critical path of a lone warp.
+    auto run = [&](auto algc) {
+    constexpr int ALG = decltype(algc)::value;
     stage(0);
     cp_async_commit();
     const int64_t nchunks = (L + kEqChunk - 1) / kEqChunk;
@@ -246,7 +252,7 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
                         o.x += qq.x; o.y += qq.y;
                     }
                 }
-            if (alg == OCB_ALG_NLMS) {
+            if constexpr (ALG == OCB_ALG_NLMS) {
 #pragma unroll
                 for (int n = 0; n < NM; ++n) {
                     float sacc = 0.f;
@@ -259,7 +265,7 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
             for (int off = LPS / 2; off > 0; off >>= 1) {
                 o.x += __shfl_xor_sync(0xffffffffu, o.x, off);
                 o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
-                if (alg == OCB_ALG_NLMS) {
+                if constexpr (ALG == OCB_ALG_NLMS) {
 #pragma unroll
                     for (int n = 0; n < NM; ++n) nrm[n] += __shfl_xor_sync(0xffffffffu, nrm[n], off);
                 }
@@ -270,13 +276,13 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
             float2 g;
             float esq;
             const float a2 = cabs2(o);
-            if (alg == OCB_ALG_CMA) {  // :826-829
+            if constexpr (ALG == OCB_ALG_CMA) {  // :826-829
                 float e = Rcma - a2;
                 g = make_float2(e * o.x, e * o.y);
                 esq = e * e;
-            } else if (alg == OCB_ALG_RDE || alg == OCB_ALG_DARDE) {  // :887-894, :953-959
+            } else if constexpr (ALG == OCB_ALG_RDE || ALG == OCB_ALG_DARDE) {  // :887-894, :953-959
                 float Rd;
-                if (alg == OCB_ALG_RDE) {
+                if constexpr (ALG == OCB_ALG_RDE) {
                     float r = sqrtf(a2);
                     float best = fabsf(rad[0] - r);
                     Rd = rad[0];
@@ -295,11 +301,11 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
                 float e = Rd * Rd - a2;
                 g = make_float2(e * o.x, e * o.y);
                 esq = e * e;
-            } else if (alg == OCB_ALG_NLMS) {  // :556
+            } else if constexpr (ALG == OCB_ALG_NLMS) {  // :556
                 float2 sr = rb[s * NM + m];
                 g = make_float2(sr.x - o.x, sr.y - o.y);
                 esq = cabs2(g);
-            } else if (alg == OCB_ALG_DDLMS) {  // :688-691  nearest constellation point, first index on ties
+            } else if constexpr (ALG == OCB_ALG_DDLMS) {  // :688-691  nearest constellation point, first index on ties
                 float best = 3.4e38f;
                 int bi = 0x7fffffff;
                 for (int c = l; c < M; c += LPS) {
@@ -324,15 +330,15 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
             if (live && l == 0) err[ind] = esq;
 
             // ---- tap update: H[m + n NM, :] += mu g conj(x_n)   (:838-840 and siblings)
-            if (alg != OCB_ALG_STATIC) {
+            if constexpr (ALG != OCB_ALG_STATIC) {
                 const float2 wg = make_float2(mu * g.x, mu * g.y);
 #pragma unroll
                 for (int n = 0; n < NM; ++n) {
-                    const float inv = (alg == OCB_ALG_NLMS) ? 1.0f / nrm[n] : 1.0f;
+                    const float inv = (ALG == OCB_ALG_NLMS) ? 1.0f / nrm[n] : 1.0f;
 #pragma unroll
                     for (int j = 0; j < TPL; ++j) {
                         float2 xin = w[n][j];
-                        if (alg == OCB_ALG_NLMS) { xin.x *= inv; xin.y *= inv; }  // :563
+                        if constexpr (ALG == OCB_ALG_NLMS) { xin.x *= inv; xin.y *= inv; }  // :563
                         float2 u = cmul_conj(wg, xin);
                         H[n][j].x += u.x; H[n][j].y += u.y;
                         if (WL) {
@@ -352,6 +358,15 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
                     }
             }
         }
+    }
+    };
+    switch (alg) {
+        case OCB_ALG_CMA: run(std::integral_constant<int, OCB_ALG_CMA>{}); break;
+        case OCB_ALG_RDE: run(std::integral_constant<int, OCB_ALG_RDE>{}); break;
+        case OCB_ALG_NLMS: run(std::integral_constant<int, OCB_ALG_NLMS>{}); break;
+        case OCB_ALG_DDLMS: run(std::integral_constant<int, OCB_ALG_DDLMS>{}); break;
+        case OCB_ALG_DARDE: run(std::integral_constant<int, OCB_ALG_DARDE>{}); break;
+        default: run(std::integral_constant<int, OCB_ALG_STATIC>{}); break;
     }
     cp_async_wait_all();
 
