@@ -229,6 +229,25 @@ int ocb_cpr_bps_run(const void* x_dev, int x_dtype, int64_t L, int nModes, const
                     int B, int Nhalf, int runFOE, double Fs, int foeM, void* y_out, void* phase_out,
                     double* fo_host, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- hard decisions and Monte-Carlo error counting ------------------------------------------------------
+ * ocb_min_euclid replaces optic.comm.modulation.minEuclid (modulation.py:271-299) and, with bits_out, the
+ * demodulateGray/demap pair (:369-408, :303-333): idx = argmin_c |x - constSymb[c]| (first index on ties),
+ * bits = binary expansion of idx, most significant bit first, log2(M) per symbol.
+ *   x_dev : n complex64/128 ; constSymb : (M) complex128 ; idx_out : n int64 or NULL ; bits_out : n*log2(M) int64 or NULL */
+int ocb_min_euclid(const void* x_dev, int x_dtype, int64_t n, const void* constSymb, int M, int64_t* idx_out,
+                   int64_t* bits_out, void* stream);
+
+/* ocb_ber_count replaces optic.comm.metrics.fastBERcalc (metrics.py:110-195) for (L, nModes) interleaved
+ * rx/tx columns on the device: rotate != 0 applies the phase-ambiguity correction mean(tx/rx) (:176-179, 'qam'
+ * and 'psk'), both are power-normalised (:181-182), SNR[dB] = 10 log10(P(tx)/P(rx - tx)) (:185), decisions on
+ * sqrtEs * x against constSymb (complex128, Gray order), BER/SER from the index XOR (:187-192).
+ *   ber/ser/snr_host : nModes doubles each (host, may be NULL) ; counts_host : [2][nModes] bit / symbol errors
+ *   (host, may be NULL).  Synchronises the stream before returning.                                      */
+int64_t ocb_ber_workspace_bytes(int nModes);
+int ocb_ber_count(const void* rx_dev, const void* tx_dev, int dtype, int64_t L, int nModes, const void* constSymb,
+                  int M, int rotate, double sqrtEs, double* ber_host, double* ser_host, double* snr_host,
+                  int64_t* counts_host, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,10 @@ SIGNATURES = {
     "ocb_cpr_workspace_bytes": (_i64, [_i64, _i]),
     "ocb_cpr_bps_run": (_i, [_vp, _i, _i64, _i, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp, C.POINTER(C.c_double), _vp,
                              _i64, _vp]),
+    "ocb_min_euclid": (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp, _vp]),
+    "ocb_ber_workspace_bytes": (_i64, [_i]),
+    "ocb_ber_count": (_i, [_vp, _vp, _i, _i64, _i, _vp, _i, _i, _d, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                           C.POINTER(C.c_double), C.POINTER(C.c_int64), _vp, _i64, _vp]),
 }
 
 

@@ -4,6 +4,7 @@
 //   coreAdaptEq + *Up      : optic/dsp/equalization.py:354-516, 520-973
 //   bps                    : optic/dsp/carrierRecovery.py:172-223
 #include <math.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -150,6 +151,20 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// NM consecutive float2 from a 32-bit shared-space address (one 128-bit access per mode pair)
+template <int NM>
+__device__ __forceinline__ void lds_window(unsigned addr, float2 (&w)[NM]) {
+    if constexpr (NM == 1) {
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w[0].x), "=f"(w[0].y) : "r"(addr));
+    } else {
+#pragma unroll
+        for (int n = 0; n < NM; n += 2)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(w[n].x), "=f"(w[n].y), "=f"(w[n + 1].x), "=f"(w[n + 1].y)
+                         : "r"(addr + 8u * n));
+    }
+}
+
 // CTA = SPB stream slots x NM tasks x LPS lanes ; thread = (slot, m, l)
 template <int NM, int TPL, int LPS, bool WL>
 __global__ void __launch_bounds__(256)
@@ -206,10 +221,32 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
     };
 
     float prev_err = 0.f;
-    constexpr int kMaxR = 8;  // radii kept in registers (16/64-QAM have 3/9 rings; more fall back to memory)
-    float rad[kMaxR];
+    // RDE ring decision without a square root on the per-symbol critical path: the radii are ascending
+    // (np.unique, equalization.py:456), so argmin_i |R_i - |o|| is the last i with |o|² > ((R_{i-1} + R_i)/2)²
+    // (a tie keeps the lower ring, like argmin).  Squared radii / thresholds of the first rings in registers
+    // (16/64-QAM have 3/9 rings); more rings fall back to memory.
+    constexpr int kMaxR = 10;
+    float rad2[kMaxR], thr2[kMaxR];
 #pragma unroll
-    for (int i = 0; i < kMaxR; ++i) rad[i] = (radii && i < nR) ? radii[i] : 3.0e38f;
+    for (int i = 0; i < kMaxR; ++i) {
+        const float ri = (radii && i < nR) ? radii[i] : 0.f;
+        const float rp = (radii && i >= 1 && i < nR) ? radii[i - 1] : 0.f;
+        const float mid = 0.5f * (rp + ri);
+        rad2[i] = ri * ri;
+        thr2[i] = (radii && i >= 1 && i < nR) ? mid * mid : 3.4e38f;
+    }
+    // window addressing: lane tap t = l + LPS*j reads row (s*SpS + t) of the staged chunk; taps beyond nTaps
+    // read a clamped (valid) row and are zeroed by a loop-invariant select
+    bool tapv[TPL];
+    unsigned tapoff[TPL];
+#pragma unroll
+    for (int j = 0; j < TPL; ++j) {
+        const int t = l + LPS * j;
+        tapv[j] = t < nTaps;
+        tapoff[j] = (unsigned)((tapv[j] ? t : nTaps - 1) * NM) * 8u;
+    }
+    const unsigned xbuf_s = (unsigned)__cvta_generic_to_shared(xbuf);
+    const unsigned sym_stride = (unsigned)(SpS * NM) * 8u;
 
     // The symbol loop is instantiated once per algorithm (compile-time ALG) so that no algorithm dispatch,
     // constant-bank reload or dead select chain sits on the per-symbol critical path of a lone warp.
@@ -223,21 +260,28 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
         __syncthreads();  // chunk k landed for every task of the CTA; chunk k-1 fully consumed
         stage(k + 1);     // lands while this chunk is processed
         cp_async_commit();
-        const float2* xb = xbuf + (k & 1) * rows_chunk * NM;
         const float2* rb = rbuf + (k & 1) * kEqChunk * NM;
         const int64_t s0 = k * kEqChunk;
         const int nsym = (int)((L - s0) < kEqChunk ? (L - s0) : kEqChunk);
 
+        // software pipeline: the window of symbol s+1 is read while symbol s goes through its reduction
+        unsigned waddr = xbuf_s + (unsigned)((k & 1) * rows_chunk * NM) * 8u;
+        float2 wn[TPL][NM];
+#pragma unroll
+        for (int j = 0; j < TPL; ++j) lds_window<NM>(waddr + tapoff[j], wn[j]);
+        float2* yp = y + (s0 * NM + m);
+        float* ep = err + s0;
+        const bool wr = live && l == 0;
         for (int s = 0; s < nsym; ++s) {
             const int64_t ind = s0 + s;
             float2 w[NM][TPL];
 #pragma unroll
-            for (int j = 0; j < TPL; ++j) {
-                const int t = l + LPS * j;
-                const float2* p = xb + (s * SpS + t) * NM;
+            for (int j = 0; j < TPL; ++j)
 #pragma unroll
-                for (int n = 0; n < NM; ++n) w[n][j] = (t < nTaps) ? p[n] : make_float2(0.f, 0.f);
-            }
+                for (int n = 0; n < NM; ++n) w[n][j] = tapv[j] ? wn[j][n] : make_float2(0.f, 0.f);
+            waddr += (s + 1 < nsym) ? sym_stride : 0u;
+#pragma unroll
+            for (int j = 0; j < TPL; ++j) lds_window<NM>(waddr + tapoff[j], wn[j]);
             // ---- filter: out_m = sum_n H[m + n NM, :] . x_n[window]   (equalization.py:464-471)
             float2 o = make_float2(0.f, 0.f);
             float nrm[NM];
@@ -270,7 +314,8 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
                     for (int n = 0; n < NM; ++n) nrm[n] += __shfl_xor_sync(0xffffffffu, nrm[n], off);
                 }
             }
-            if (live && l == 0) y[ind * NM + m] = o;  // equalization.py:473
+            if (wr) *yp = o;  // equalization.py:473
+            yp += NM;
 
             // ---- error term g and squared error, per algorithm
             float2 g;
@@ -282,23 +327,25 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
                 esq = e * e;
             } else if constexpr (ALG == OCB_ALG_RDE || ALG == OCB_ALG_DARDE) {  // :887-894, :953-959
                 float Rd;
+                float Rd2;
                 if constexpr (ALG == OCB_ALG_RDE) {
-                    float r = sqrtf(a2);
-                    float best = fabsf(rad[0] - r);
-                    Rd = rad[0];
+                    Rd2 = rad2[0];
+                    if (nR <= 4) {  // uniform branch: QPSK / 16-QAM / 16-APSK need three selects, not nine
 #pragma unroll
-                    for (int i = 1; i < kMaxR; ++i) {
-                        float dd = fabsf(rad[i] - r);
-                        if (dd < best) { best = dd; Rd = rad[i]; }
-                    }
-                    for (int i = kMaxR; i < nR; ++i) {
-                        float dd = fabsf(radii[i] - r);
-                        if (dd < best) { best = dd; Rd = radii[i]; }
+                        for (int i = 1; i < 4; ++i) Rd2 = (a2 > thr2[i]) ? rad2[i] : Rd2;
+                    } else {
+#pragma unroll
+                        for (int i = 1; i < kMaxR; ++i) Rd2 = (a2 > thr2[i]) ? rad2[i] : Rd2;
+                        for (int i = kMaxR; i < nR; ++i) {
+                            const float ri = radii[i], mid = 0.5f * (radii[i - 1] + ri);
+                            if (a2 > mid * mid) Rd2 = ri * ri;
+                        }
                     }
                 } else {
                     Rd = sqrtf(cabs2(rb[s * NM + m]));
+                    Rd2 = Rd * Rd;
                 }
-                float e = Rd * Rd - a2;
+                float e = Rd2 - a2;
                 g = make_float2(e * o.x, e * o.y);
                 esq = e * e;
             } else if constexpr (ALG == OCB_ALG_NLMS) {  // :556
@@ -327,7 +374,8 @@ k_mimo_eq(const float2* __restrict__ X, const float2* __restrict__ REF, float2* 
                 esq = prev_err;
             }
             prev_err = esq;
-            if (live && l == 0) err[ind] = esq;
+            if (wr) *ep = esq;
+            ++ep;
 
             // ---- tap update: H[m + n NM, :] += mu g conj(x_n)   (:838-840 and siblings)
             if constexpr (ALG != OCB_ALG_STATIC) {
@@ -390,7 +438,9 @@ int launch_mimo(bool wl, cudaStream_t st, const float2* X, const float2* REF, fl
                 int64_t es, int64_t ems, int64_t L, int nTaps,
                 int SpS, int alg, float mu, const float2* cs, int M, const float* radii, int nR, float Rcma) {
     // stream slots per CTA: one in latency mode (CTA = NM warps), up to 128 threads' worth otherwise
-    const int spb = (LPS == 32) ? 1 : (128 / (LPS * NM) > 0 ? 128 / (LPS * NM) : 1);
+    int spb = (LPS == 32) ? 1 : (128 / (LPS * NM) > 0 ? 128 / (LPS * NM) : 1);
+    if (spb > nStreams) spb = nStreams;
+    if (spb * LPS * NM < 32) spb = 32 / (LPS * NM);  // never launch a partial warp (dead slots shadow the last stream)
     const int grid = (nStreams + spb - 1) / spb;
     const int block = spb * NM * LPS;
     const int rows_chunk = (kEqChunk - 1) * SpS + nTaps;
@@ -432,7 +482,11 @@ extern "C" int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hw
     // nTaps <= 32 — the per-symbol instruction count is what bounds a lone stream.  Many streams
     // (throughput mode): 8 lanes x 4 taps, four streams per warp, 3 shuffle stages instead of 5.
     const bool many = nStreams >= 4 * kNumSMs;
-    const int lps = (many && nTaps <= 32) ? 8 : ((many && nTaps <= 64) ? 16 : 32);
+    int lps = (many && nTaps <= 32) ? 8 : ((many && nTaps <= 64) ? 16 : 32);
+    if (const char* e = getenv("OCB_EQ_LPS")) {  // tuning override (8, 16 or 32 lanes per task)
+        const int v = atoi(e);
+        if ((v == 8 || v == 16 || v == 32) && (nTaps + v - 1) / v <= 4 && (v == 32 || (nTaps + v - 1) / v >= (v == 16 ? 2 : 1))) lps = v;
+    }
     const int tpl = (nTaps + lps - 1) / lps;
 #define OCB_MIMO_CASE(NM_, TPL_, LPS_)                                                                         \
     if (nModes == NM_ && lps == LPS_ && tpl == TPL_)                                                           \
@@ -446,6 +500,7 @@ extern "C" int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hw
     OCB_MIMO_CASE(4, 1, 32) OCB_MIMO_CASE(4, 2, 32)
     OCB_MIMO_CASE(1, 1, 8) OCB_MIMO_CASE(1, 2, 8) OCB_MIMO_CASE(1, 3, 8) OCB_MIMO_CASE(1, 4, 8)
     OCB_MIMO_CASE(2, 1, 8) OCB_MIMO_CASE(2, 2, 8) OCB_MIMO_CASE(2, 3, 8) OCB_MIMO_CASE(2, 4, 8)
+    OCB_MIMO_CASE(1, 2, 16) OCB_MIMO_CASE(2, 2, 16)
     OCB_MIMO_CASE(1, 3, 16) OCB_MIMO_CASE(1, 4, 16) OCB_MIMO_CASE(2, 3, 16) OCB_MIMO_CASE(2, 4, 16)
 #undef OCB_MIMO_CASE
     return fail("mimo_eq_run: unsupported (nModes, nTaps) combination", __FILE__, __LINE__);

@@ -75,3 +75,45 @@ def normalizedConstellation(M, constType, shapingFactor=0.0, prec=None):
     px = px / np.sum(px)
     c /= np.sqrt(np.sum(np.abs(c) ** 2 * px))
     return c
+
+
+def _device_decisions(symb, const, want_idx, want_bits):
+    """Run ``ocb_min_euclid`` on ``symb`` (any real/complex array) against ``const``; int64 outputs."""
+    import ctypes as C
+
+    from . import _cabi, _engine
+    torch = _cabi.require_cuda()
+    lib = _cabi.lib()
+    x = _engine.as_host_complex(np.asarray(symb).reshape(-1))
+    c = np.ascontiguousarray(np.asarray(const).reshape(-1).astype(np.complex128))
+    n, M = x.shape[0], c.shape[0]
+    nbits = int(np.log2(M))
+    d_x = torch.from_numpy(x.view(np.float32 if x.dtype == np.complex64 else np.float64)).to("cuda")
+    d_c = torch.from_numpy(c.view(np.float64)).to("cuda")
+    d_idx = torch.empty(n, dtype=torch.int64, device="cuda") if want_idx else None
+    d_bits = torch.empty(n * nbits, dtype=torch.int64, device="cuda") if want_bits else None
+    vp = C.c_void_p
+    _cabi.check(
+        lib.ocb_min_euclid(vp(d_x.data_ptr()), _engine.dtype_tag(x.dtype), n, vp(d_c.data_ptr()), M,
+                           vp(d_idx.data_ptr() if want_idx else None), vp(d_bits.data_ptr() if want_bits else None),
+                           vp(_cabi.stream_ptr(torch))),
+        "ocb_min_euclid",
+    )
+    return (d_idx.cpu().numpy() if want_idx else None), (d_bits.cpu().numpy() if want_bits else None)
+
+
+def minEuclid(symb, const):
+    """Index of the closest constellation symbol for every entry of ``symb`` (1-D), on the GPU.
+
+    Mirror of ``optic.comm.modulation.minEuclid`` (modulation.py:271-299): int64 indices, first index on
+    exact ties.  Distances are evaluated in float64 for every input dtype.
+    """
+    return _device_decisions(symb, const, True, False)[0]
+
+
+def demodulateGray(symb, M, constType):
+    """Hard-decision demodulation to bits (modulation.py:369-408) on the GPU: log2(M) bits per symbol, most
+    significant first, as an int64 array like the reference's ``dtype="int"``."""
+    if M != 2 and constType == "ook":
+        M = 2
+    return _device_decisions(symb, grayMapping(M, constType), False, True)[1]

@@ -21,6 +21,14 @@ def golden():
         return {k: z[k] for k in z.files}
 
 
+@pytest.fixture(scope="session")
+def golden_metrics():
+    """Reference decisions / error counts on seeded inputs (tests/golden/make_golden_metrics.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_metrics.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
 def rel_l2(a, b):
     a = np.asarray(a)
     b = np.asarray(b)
