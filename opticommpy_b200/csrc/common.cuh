@@ -48,6 +48,25 @@ int64_t& launch_counter();
         OCB_CUDA(cudaGetLastError());                                               \
     } while (0)
 
+// Launch with programmatic dependent launch allowed: the kernel may be scheduled while its predecessor
+// in the stream drains; it must execute pdl_wait() before it touches anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define OCB_LAUNCH_PDL(kernel, grid, block, smem, stream, pdl, ...)                  \
+    do {                                                                            \
+        ::ocb::launch_counter()++;                                                  \
+        OCB_CUDA(::ocb::launch_ex(kernel, (grid), (block), (smem), (stream), (pdl), __VA_ARGS__)); \
+    } while (0)
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 inline int grid_for(int64_t work_items, int block, int per_thread, int max_waves = 8) {
@@ -59,6 +78,11 @@ inline int grid_for(int64_t work_items, int block, int per_thread, int max_waves
 }
 
 // ---- device helpers ------------------------------------------------------------------------
+// Programmatic dependent launch: wait until the preceding kernel of the stream has completed and its
+// writes are visible (no-op when the launch did not allow PDL) / let the next kernel be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -113,6 +137,18 @@ __device__ __forceinline__ float ld_stream(const float* p) {
 __device__ __forceinline__ float2 ld_stream_ordered(const float2* p) {
     float2 v;
     asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+// Same loads with a fixed position in the instruction stream (volatile, no memory clobber): used where a
+// batch of loads must be issued together ahead of the code that consumes it.
+__device__ __forceinline__ float2 ld_stream_pinned(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_pinned(const float* p) {
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void st_stream(float2* p, float2 v) {

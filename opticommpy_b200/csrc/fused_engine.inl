@@ -5,10 +5,16 @@ namespace {
 
 constexpr int kFreqC = 8;  // W positions per k_freq tile (64-byte row segments)
 
+// programmatic dependent launch between the passes of the step loop (OCB_PDL=0 disables; tuning knob)
+bool pdl_enabled() {
+    const char* v = getenv("OCB_PDL");
+    return !(v && atoi(v) == 0);
+}
+
 template <int Q1, int NP, int MODE>
 int launch_time_t(const TimeArgs& a, cudaStream_t st) {
     const int tasks_per_cta = 64 / Q1;
-    OCB_LAUNCH((k_time<Q1, NP, MODE>), a.N2 * NP / tasks_per_cta, 64, 0, st, a);
+    OCB_LAUNCH_PDL((k_time<Q1, NP, MODE>), a.N2 * NP / tasks_per_cta, 64, 0, st, pdl_enabled(), a);
     return 0;
 }
 template <int NP, int MODE>
@@ -30,7 +36,7 @@ int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP,
         OCB_CUDA(cudaFuncSetAttribute(k_freq<Q2, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    OCB_LAUNCH((k_freq<Q2, C>), NP * N1 / C, Q2 * C, smem, st, W, LP, tw, N1, flag, step_id);
+    OCB_LAUNCH_PDL((k_freq<Q2, C>), NP * N1 / C, Q2 * C, smem, st, pdl_enabled(), W, LP, tw, N1, flag, step_id);
     return 0;
 }
 int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st,
@@ -91,6 +97,39 @@ int launch_freq_s(float2* W, const float2* LP, const float2* tw, int N1, int NP,
     return 0;
 }
 
+// persistent pipelined time kernels (N1 = 1024, both polarisations): fused_pipe_kernels.cuh
+struct PipeKnobs {
+    bool time_on;     // OCB_TPIPE=0 falls back to the one-wave k_time
+    bool stage_h;     // OCB_TPIPE_SH: E_hd / P_ch rows staged through shared memory too
+    int ctas_iter, ctas_first, ctas_fwd;  // grid sizes (0: default = resident CTAs x 148)
+};
+PipeKnobs read_pipe_knobs() {
+    auto geti = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
+    PipeKnobs k;
+    k.time_on = geti("OCB_TPIPE", 0) != 0;  // measured slower than the one-wave kernels (6 warps per SM): off by default
+    k.stage_h = geti("OCB_TPIPE_SH", 1) != 0;
+    k.ctas_iter = geti("OCB_TPIPE_GRID_ITER", 0);
+    k.ctas_first = geti("OCB_TPIPE_GRID_FIRST", 0);
+    k.ctas_fwd = geti("OCB_TPIPE_GRID_FWD", 0);
+    return k;
+}
+template <int MODE, bool SH>
+int launch_time_p(const TimeArgs& a, int grid, cudaStream_t st) {
+    using Cfg = TimePipeCfg<MODE, SH>;
+    static bool configured = false;
+    if (!configured) {
+        OCB_CUDA(cudaFuncSetAttribute(k_time_p<MODE, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    if (grid <= 0) {
+        const int resident = (227 * 1024) / (Cfg::SMEM_BYTES + 2048);  // 1 KB reserved per CTA + static reduction scratch
+        grid = kNumSMs * resident;
+    }
+    if (grid > a.N2) grid = a.N2;
+    OCB_LAUNCH((k_time_p<MODE, SH>), grid, 64, Cfg::SMEM_BYTES, st, a);
+    return 0;
+}
+
 TimeArgs time_base(ocb_ssfm_plan* p) {
     TimeArgs a{};
     a.tw = p->tw1; a.tabV = p->tabV; a.tabU = p->tabU;
@@ -111,6 +150,8 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
     const size_t field_bytes = (size_t)R * N * sizeof(float2);
     if (fused_init_tables(p, st)) return 1;
     const bool split = p->split;
+    const PipeKnobs pk = read_pipe_knobs();
+    const bool tpipe = pk.time_on && !split && p->q1 == 32;
     // One field buffer: k_time<TM_ITER> replaces the previous iterate by the new one in place, which keeps
     // the per-iteration working set (W, E_c, E_hd, P_ch, operator table = 60 MB at N = 2^20) inside L2.
     float2* bufs[3] = {p->A, p->A, p->A};
@@ -172,7 +213,8 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 ProfScope ps(p, 2, st);
                 TimeArgs c0 = time_base(p);
                 c0.in = bufs[cur]; c0.out = Wb;
-                if (split ? launch_time_s<TM_FWD>(c0, st) : launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
+                if (tpipe ? launch_time_p<TM_FWD, false>(c0, pk.ctas_fwd, st)
+                          : split ? launch_time_s<TM_FWD>(c0, st) : launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
                 if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st) : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st)) return 1;
             }
             {
@@ -180,7 +222,8 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 TimeArgs c1 = time_base(p);
                 c1.in = Wb; c1.out = Wb; c1.aux0 = bufs[cur]; c1.aux1 = p->Ehd; c1.pch = p->Pch;
                 c1.cphi = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma);
-                if (split ? launch_time_s<TM_FIRST>(c1, st) : launch_time<2, TM_FIRST>(p->q1, c1, st)) return 1;
+                if (tpipe ? launch_time_p<TM_FIRST, false>(c1, pk.ctas_first, st)
+                          : split ? launch_time_s<TM_FIRST>(c1, st) : launch_time<2, TM_FIRST>(p->q1, c1, st)) return 1;
             }
             int ec = cur, dst = (cur + 1) % 3;
             // Fixed-point loop (channels.py:413).  Iteration it+1 is enqueued BEFORE the outcome of
@@ -201,6 +244,8 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 ci.cphi = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma * 0.5);
                 ci.ext.mail = p->d_mail; ci.ext.converged_step = p->conv_flag; ci.ext.step_id = step_id;
                 ci.ext.seq = seq; ci.ext.tol = q->tol;
+                if (tpipe) return pk.stage_h ? launch_time_p<TM_ITER, true>(ci, pk.ctas_iter, st)
+                                             : launch_time_p<TM_ITER, false>(ci, pk.ctas_iter, st);
                 return split ? launch_time_s<TM_ITER>(ci, st) : launch_time<2, TM_ITER>(p->q1, ci, st);  // :424, :436, :414-417
             };
             unsigned long long seq_cur = ++p->mail_seq;

@@ -53,15 +53,11 @@ struct TimeArgs {
 // CTA and share |E|^2 through shared memory.  Every global access is lane-contiguous.
 // ------------------------------------------------------------------------------------------
 template <int Q1, int NP, int MODE>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 7)
 k_time(const TimeArgs A) {
     using namespace fft;
     constexpr int G = 32 / Q1, N1 = 32 * Q1, TASKS = 64 / Q1;
     constexpr int STR = Q1 + 1, GBUF = 32 * STR + (Q1 < 32 ? Q1 : 0);
-    if constexpr (MODE == TM_ITER) {
-        // speculative launch of an iteration whose predecessor already converged: nothing to do
-        if (A.ext.mail && *reinterpret_cast<volatile long long*>(A.ext.converged_step) == A.ext.step_id) return;
-    }
     __shared__ float xbuf[TASKS * 2 * GBUF];
     __shared__ float pbuf[(MODE == TM_FIRST || MODE == TM_ITER) ? TASKS * N1 : 1];
 
@@ -93,6 +89,15 @@ k_time(const TimeArgs A) {
                 for (int l = t; l < LINES / 2; l += Q1)
                     prefetch_l2(reinterpret_cast<const char*>(A.pch + (int64_t)row * N1) + l * 128);
         }
+    }
+
+    // Everything above only touched tables and issued prefetch hints; the field data below may have been
+    // written by the preceding kernel of the stream (programmatic dependent launch).
+    pdl_wait();
+    pdl_launch_dependents();
+    if constexpr (MODE == TM_ITER) {
+        // speculative launch of an iteration whose predecessor already converged: nothing to do
+        if (A.ext.mail && *reinterpret_cast<volatile long long*>(A.ext.converged_step) == A.ext.step_id) return;
     }
 
     // ---- enter ----------------------------------------------------------------------------------
@@ -162,9 +167,19 @@ k_time(const TimeArgs A) {
                 }
             }
         }
-        __syncthreads();
         float* pch = A.pch + (int64_t)row * N1;
-        const float2* ehd = (MODE == TM_ITER) ? A.ehd + base : nullptr;
+        float pc[MODE == TM_ITER ? 32 : 1];
+        if constexpr (MODE == TM_ITER) {
+            // E_fd has been stored, so v[] is free: fetch the whole E_hd and P_ch rows in one batch (64
+            // loads in flight per thread) before the barrier.  The rotation loop below contains a branch
+            // (large-phase path), which would otherwise make every trip wait for its own two loads.
+            const float2* ehd = A.ehd + base;
+#pragma unroll
+            for (int a = 0; a < 32; ++a) v[a] = ld_stream_pinned(ehd + Q1 * a + t);
+#pragma unroll
+            for (int a = 0; a < 32; ++a) pc[a] = ld_stream_pinned(pch + Q1 * a + t);
+        }
+        __syncthreads();
 #pragma unroll
         for (int a = 0; a < 32; ++a) {
             const float P = pown[Q1 * a + t] + poth[Q1 * a + t];
@@ -174,8 +189,7 @@ k_time(const TimeArgs A) {
                 ph = A.cphi * P;  // φ = (8/9)γ(P+P)/2, channels.py:390/493 with E_conv == Ech
             } else {
                 s_max = fmaxf(s_max, P);
-                ph = A.cphi * (ld_stream(pch + Q1 * a + t) + P);  // channels.py:436
-                v[a] = ld_stream(ehd + Q1 * a + t);
+                ph = A.cphi * (pc[a] + P);  // channels.py:436
             }
             v[a] = cmul(v[a], phase_rot(ph));  // channels.py:414-417
         }
@@ -211,7 +225,6 @@ __global__ void __launch_bounds__(Q2* C, (Q2 * C <= 256) ? 2 : 1)
 k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __restrict__ tw, int N1,
        const long long* __restrict__ converged_step, long long step_id) {
     using namespace fft;
-    if (converged_step && *reinterpret_cast<const volatile long long*>(converged_step) == step_id) return;
     constexpr int STR = Q2 * C + C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xr = reinterpret_cast<float*>(smem_raw);  // [32*STR]
@@ -230,6 +243,9 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
         constexpr int LINES = 32 * Q2 * C * 8 / 128;
         for (int l = tid; l < LINES; l += Q2 * C) prefetch_l2(lp_tile + l * 128);
     }
+    pdl_wait();  // W was written by the preceding time pass (programmatic dependent launch)
+    pdl_launch_dependents();
+    if (converged_step && *reinterpret_cast<const volatile long long*>(converged_step) == step_id) return;
     float2 v[32];
 #pragma unroll
     for (int a = 0; a < 32; ++a) v[a] = ld_stream(base + (int64_t)(Q2 * a + q) * N1);

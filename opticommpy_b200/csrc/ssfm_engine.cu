@@ -14,6 +14,7 @@
 #include "ssfm_kernels.cuh"
 #include "fused_kernels.cuh"
 #include "fused_split_kernels.cuh"
+#include "fused_pipe_kernels.cuh"
 
 using namespace ocb;
 

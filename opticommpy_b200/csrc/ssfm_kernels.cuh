@@ -72,7 +72,8 @@ struct FinalizeExt {
     double tol;
 };
 
-__device__ __forceinline__ void block_reduce3_finalize(float s0, float s1, float m,
+template <typename TS>  // float: one row per thread ; double: persistent kernels that sum several rows per thread
+__device__ __forceinline__ void block_reduce3_finalize(TS s0, TS s1, float m,
                                                        double* __restrict__ partials,
                                                        double* __restrict__ out,
                                                        unsigned* __restrict__ ticket,
@@ -80,8 +81,9 @@ __device__ __forceinline__ void block_reduce3_finalize(float s0, float s1, float
     __shared__ double sh0[32], sh1[32], sh2[32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    // warp level in float (<= 32 addends), block level in double
-    float w0 = warp_sum(s0), w1 = warp_sum(s1), wm = warp_max(m);
+    // warp level in the caller's type (float: <= 32 addends), block level in double
+    TS w0 = warp_sum(s0), w1 = warp_sum(s1);
+    float wm = warp_max(m);
     if (lane == 0) { sh0[wid] = (double)w0; sh1[wid] = (double)w1; sh2[wid] = (double)wm; }
     __syncthreads();
     if (wid == 0) {
