@@ -28,23 +28,24 @@ int launch_time(int Q1, const TimeArgs& a, cudaStream_t st) {
 }
 template <int Q2>
 int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP, const long long* flag,
-                  long long step_id, cudaStream_t st) {
+                  long long step_id, const long long* need_flag, long long need_id, cudaStream_t st) {
     static bool configured = false;
     constexpr int C = kFreqC;
-    const size_t smem = (size_t)2 * 32 * (Q2 * C + C) * sizeof(float);
+    const size_t smem = (size_t)2 * 32 * (Q2 * C + C) * sizeof(float) + (size_t)2 * 32 * Q2 * sizeof(float2);
     if (!configured) {
         OCB_CUDA(cudaFuncSetAttribute(k_freq<Q2, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    OCB_LAUNCH_PDL((k_freq<Q2, C>), NP * N1 / C, Q2 * C, smem, st, pdl_enabled(), W, LP, tw, N1, flag, step_id);
+    OCB_LAUNCH_PDL((k_freq<Q2, C>), NP * N1 / C, Q2 * C, smem, st, pdl_enabled(), W, LP, tw, N1, flag, step_id, need_flag, need_id);
     return 0;
 }
 int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st,
-                const long long* flag = nullptr, long long step_id = 0) {
+                const long long* flag = nullptr, long long step_id = 0, const long long* need_flag = nullptr,
+                long long need_id = 0) {
     switch (Q2) {
-        case 8: return launch_freq_t<8>(W, LP, tw, N1, NP, flag, step_id, st);
-        case 16: return launch_freq_t<16>(W, LP, tw, N1, NP, flag, step_id, st);
-        case 32: return launch_freq_t<32>(W, LP, tw, N1, NP, flag, step_id, st);
+        case 8: return launch_freq_t<8>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
+        case 16: return launch_freq_t<16>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
+        case 32: return launch_freq_t<32>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
     }
     return fail("fused engine: unsupported N2", __FILE__, __LINE__);
 }
@@ -162,6 +163,10 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
     double table_h = NAN;
     int next_save = 0;
     uint64_t amp_calls = 0;
+    const bool predict = !(getenv("OCB_PREDICT") && atoi(getenv("OCB_PREDICT")) == 0);
+    int last_iters = -1;            // iterations of the previous step of this span (-1: unknown)
+    bool chained = false;           // first half + iteration 0 of the coming step are already enqueued
+    unsigned long long chained_seq = 0;
 
     // keep the operator tables (read by every k_freq launch) resident in L2
     {
@@ -193,6 +198,7 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
             maxP = p->h_sums[2];
         }
         double z = 0.0;
+        last_iters = -1;  // the amplifier changed the power: no prediction for the first step of a span
         while (z < q->Lspan) {  // channels.py:387
             double hz_;
             if (q->nlprMethod) {  // channels.py:392-397
@@ -207,72 +213,130 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 if (launch_linop_perm(p, LP, a, b, q->Fs, hz_ / 2.0, 1.0 / (double)N, st, split)) return 1;
                 table_h = hz_;
             }
-            // first half step (channels.py:409-410): time pass forward, frequency pass with L, then the
-            // time pass that completes the inverse, stores E_hd / Pch, rotates and goes forward again
-            {
-                ProfScope ps(p, 2, st);
-                TimeArgs c0 = time_base(p);
-                c0.in = bufs[cur]; c0.out = Wb;
-                if (tpipe ? launch_time_p<TM_FWD, false>(c0, pk.ctas_fwd, st)
-                          : split ? launch_time_s<TM_FWD>(c0, st) : launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
-                if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st) : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st)) return 1;
-            }
-            {
-                ProfScope ps(p, 1, st);
-                TimeArgs c1 = time_base(p);
-                c1.in = Wb; c1.out = Wb; c1.aux0 = bufs[cur]; c1.aux1 = p->Ehd; c1.pch = p->Pch;
-                c1.cphi = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma);
-                if (tpipe ? launch_time_p<TM_FIRST, false>(c1, pk.ctas_first, st)
-                          : split ? launch_time_s<TM_FIRST>(c1, st) : launch_time<2, TM_FIRST>(p->q1, c1, st)) return 1;
-            }
-            int ec = cur, dst = (cur + 1) % 3;
-            // Fixed-point loop (channels.py:413).  Iteration it+1 is enqueued BEFORE the outcome of
-            // iteration it is known; the finalising block of it sets a device flag when lim < tol and
-            // the speculative launches of the same step exit at once.  The host only reads a mailbox
-            // in mapped pinned memory, so the GPU never waits for a stream synchronisation.
+            // ---- one SSFM step --------------------------------------------------------------------------
+            // Launch protocol (no stream synchronisation anywhere):
+            //  * iteration it+1 is enqueued BEFORE the outcome of iteration it is known; the finalising block
+            //    of `it` sets a device flag when lim < tol and the speculative launches of the same step exit.
+            //  * PREDICTION: in a fixed-step span the iteration count hardly ever changes from one step to the
+            //    next.  The iteration predicted to be the last one (index `pred`) runs as TM_ITERF, which
+            //    transforms the new iterate itself, and the first half (+ iteration 0) of the NEXT step is
+            //    enqueued behind it, guarded by a second flag that TM_ITERF sets only if it did converge.  A
+            //    right prediction saves the TM_FWD pass and the E_hd/P_ch traffic of the last iteration; a wrong
+            //    one costs a few empty launches plus the TM_ROT recovery pass.  Decisions (lim < tol) and
+            //    arithmetic are those of the plain flow, so step/iteration counts and fields are unchanged.
             const long long step_id = ++p->step_counter;
             const bool speculate = !p->prof_on;
-            auto enqueue_iter = [&](int e_c, int d_st, unsigned long long seq) -> int {
+            const float cphi_first = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma);
+            const float cphi_iter = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma * 0.5);
+            auto time_args_iter = [&](long long sid, unsigned long long seq, bool final_pred, const long long* need,
+                                      long long need_id) {
+                TimeArgs ci = time_base(p);
+                ci.in = Wb; ci.out = Wb; ci.aux0 = p->A; ci.aux1 = p->A; ci.ehd = p->Ehd; ci.pch = p->Pch;
+                ci.cphi = cphi_iter;
+                ci.ext.mail = p->d_mail; ci.ext.converged_step = p->conv_flag; ci.ext.step_id = sid;
+                ci.ext.seq = seq; ci.ext.tol = q->tol;
+                ci.ext.final_step = final_pred ? p->final_flag : nullptr;
+                ci.need_flag = need; ci.need_id = need_id;
+                return ci;
+            };
+            // k_freq + time pass of one fixed-point iteration (channels.py:420-421, 424, 436, 414-417)
+            auto enqueue_iter = [&](long long sid, unsigned long long seq, bool final_pred, const long long* need,
+                                    long long need_id) -> int {
                 {
                     ProfScope ps(p, 2, st);
-                    if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st, p->conv_flag, step_id)
-                              : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, p->conv_flag, step_id)) return 1;  // :420-421
+                    if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st, p->conv_flag, sid)
+                              : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, p->conv_flag, sid, need, need_id)) return 1;
                 }
                 ProfScope ps(p, 0, st);
-                TimeArgs ci = time_base(p);
-                ci.in = Wb; ci.out = Wb; ci.aux0 = bufs[e_c]; ci.aux1 = bufs[d_st]; ci.ehd = p->Ehd; ci.pch = p->Pch;
-                ci.cphi = (float)(dir * hz_ * (8.0 / 9.0) * q->gamma * 0.5);
-                ci.ext.mail = p->d_mail; ci.ext.converged_step = p->conv_flag; ci.ext.step_id = step_id;
-                ci.ext.seq = seq; ci.ext.tol = q->tol;
+                const TimeArgs ci = time_args_iter(sid, seq, final_pred, need, need_id);
                 if (tpipe) return pk.stage_h ? launch_time_p<TM_ITER, true>(ci, pk.ctas_iter, st)
                                              : launch_time_p<TM_ITER, false>(ci, pk.ctas_iter, st);
-                return split ? launch_time_s<TM_ITER>(ci, st) : launch_time<2, TM_ITER>(p->q1, ci, st);  // :424, :436, :414-417
+                if (split) return launch_time_s<TM_ITER>(ci, st);
+                return final_pred ? launch_time<2, TM_ITERF>(p->q1, ci, st) : launch_time<2, TM_ITER>(p->q1, ci, st);
             };
-            unsigned long long seq_cur = ++p->mail_seq;
-            if (enqueue_iter(ec, dst, seq_cur)) return 1;
+            // first half step from the frequency-side buffer (channels.py:409-410 after the forward time pass):
+            // frequency pass with L, then the time pass that completes the inverse, stores E_hd / Pch and rotates
+            auto enqueue_first_half = [&](bool with_fwd, const long long* need, long long need_id) -> int {
+                {
+                    ProfScope ps(p, 2, st);
+                    if (with_fwd) {
+                        TimeArgs c0 = time_base(p);
+                        c0.in = p->A; c0.out = Wb;
+                        if (tpipe ? launch_time_p<TM_FWD, false>(c0, pk.ctas_fwd, st)
+                                  : split ? launch_time_s<TM_FWD>(c0, st) : launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
+                    }
+                    if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st)
+                              : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, nullptr, 0, need, need_id)) return 1;
+                }
+                ProfScope ps(p, 1, st);
+                TimeArgs c1 = time_base(p);
+                c1.in = Wb; c1.out = Wb; c1.aux0 = p->A; c1.aux1 = p->Ehd; c1.pch = p->Pch;
+                c1.cphi = cphi_first;
+                c1.need_flag = need; c1.need_id = need_id;
+                return tpipe ? launch_time_p<TM_FIRST, false>(c1, pk.ctas_first, st)
+                             : split ? launch_time_s<TM_FIRST>(c1, st) : launch_time<2, TM_FIRST>(p->q1, c1, st);
+            };
+
+            const bool can_predict = predict && speculate && !split && !tpipe && !q->nlprMethod;
+            int pred = (can_predict && last_iters >= 1 && last_iters <= q->maxIter) ? last_iters - 1 : -1;
+            unsigned long long seq_cur;
+            if (chained) {  // first half and iteration 0 of this step were enqueued behind the previous TM_ITERF
+                seq_cur = chained_seq;
+                chained = false;
+            } else {
+                if (enqueue_first_half(true, nullptr, 0)) return 1;
+                seq_cur = ++p->mail_seq;
+                if (enqueue_iter(step_id, seq_cur, pred == 0, nullptr, 0)) return 1;
+            }
+            int iters_this_step = 0;
             for (int it = 0; it < q->maxIter; ++it) {
                 unsigned long long seq_next = 0;
-                const int third = 3 - ec - dst;
-                if (speculate && it + 1 < q->maxIter) {
+                bool next_enqueued = false;
+                if (it == pred) {
+                    // TM_ITERF is in flight: chain the next step behind it if that step uses the same operator table
+                    double zn = z + hz_;
+                    const bool next_same = (zn < q->Lspan) && !(q->Lspan - zn < q->hz) && (q->hz == hz_);
+                    if (next_same) {
+                        const long long next_id = p->step_counter + 1;
+                        if (enqueue_first_half(false, p->final_flag, step_id)) return 1;
+                        chained_seq = ++p->mail_seq;
+                        if (enqueue_iter(next_id, chained_seq, pred == 0, p->final_flag, step_id)) return 1;
+                        chained = true;
+                    }
+                } else if (speculate && it + 1 < q->maxIter) {
                     seq_next = ++p->mail_seq;
-                    if (enqueue_iter(dst, third, seq_next)) return 1;
+                    if (enqueue_iter(step_id, seq_next, it + 1 == pred, nullptr, 0)) return 1;
+                    next_enqueued = true;
                 }
                 if (wait_mail(p, seq_cur, st)) return 1;
                 const double lim = sqrt(p->h_sums[0]) / sqrt(p->h_sums[1]);  // channels.py:517-519
                 const bool converged = p->h_sums[3] != 0.0;  // the device's decision (same formula, same doubles)
                 S.iterations++;
+                iters_this_step++;
                 S.last_lim = lim;
-                ec = dst;  // Ex_conv = Ech_x_fd (channels.py:426-427)
-                dst = third;
-                if (converged) break;                        // channels.py:429
+                if (converged) {  // channels.py:429
+                    if (it != pred) chained = false;
+                    break;
+                }
+                if (it == pred) {
+                    // wrong prediction: the chained launches exit on the flag; redo the second half of a plain
+                    // iteration (rotation of E_hd with the new phase + forward time pass)
+                    chained = false;
+                    pred = -1;
+                    if (it < q->maxIter - 1) {
+                        TimeArgs cr = time_base(p);
+                        cr.out = Wb; cr.aux0 = p->A; cr.ehd = p->Ehd; cr.pch = p->Pch; cr.cphi = cphi_iter;
+                        if (launch_time<2, TM_ROT>(p->q1, cr, st)) return 1;
+                    }
+                }
                 if (it == q->maxIter - 1) { S.nonconverged++; break; }  // channels.py:431-434
-                if (!speculate) {
+                if (!next_enqueued) {
                     seq_next = ++p->mail_seq;
-                    if (enqueue_iter(ec, dst, seq_next)) return 1;
+                    if (enqueue_iter(step_id, seq_next, it + 1 == pred, nullptr, 0)) return 1;
                 }
                 seq_cur = seq_next;
             }
-            cur = ec;
+            last_iters = iters_this_step;
             maxP = p->h_sums[2];
             z += hz_;
             S.steps++;

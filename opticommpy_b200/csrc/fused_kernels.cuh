@@ -25,7 +25,13 @@
 
 namespace ocb {
 
-enum TimeMode { TM_FWD = 0, TM_INV = 1, TM_FIRST = 2, TM_ITER = 3, TM_NLSE = 4 };
+// TM_ITERF: an iteration that the host predicts to be the last one of its step.  It does everything
+//           TM_ITER does up to the convergence sums and the store of the new iterate, but then transforms
+//           that iterate itself (the next step starts from it, channels.py:438-439 + :409) instead of the
+//           re-rotated E_hd, which saves the separate TM_FWD pass of the next step.
+// TM_ROT  : recovery when that prediction was wrong: rotate E_hd with the phase of the stored iterate
+//           (channels.py:436, 414-417) and transform it, i.e. the second half of TM_ITER.
+enum TimeMode { TM_FWD = 0, TM_INV = 1, TM_FIRST = 2, TM_ITER = 3, TM_NLSE = 4, TM_ITERF = 5, TM_ROT = 6 };
 
 struct TimeArgs {
     const float2* in;     // TM_FWD: time-domain field ; others: W buffer
@@ -45,6 +51,8 @@ struct TimeArgs {
     float cphi;           // dir*hz*(8/9)γ (FIRST) | dir*hz*(8/9)γ/2 (ITER) | γ hz (NLSE)
     float out_scale;      // TM_INV: gain applied to the time-domain output
     FinalizeExt ext;      // TM_ITER: host mailbox + convergence flag (ext.mail == nullptr: unused)
+    const long long* need_flag;  // speculative launch across a step boundary: run only if *need_flag == need_id
+    long long need_id;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -59,7 +67,9 @@ k_time(const TimeArgs A) {
     constexpr int G = 32 / Q1, N1 = 32 * Q1, TASKS = 64 / Q1;
     constexpr int STR = Q1 + 1, GBUF = 32 * STR + (Q1 < 32 ? Q1 : 0);
     __shared__ float xbuf[TASKS * 2 * GBUF];
-    __shared__ float pbuf[(MODE == TM_FIRST || MODE == TM_ITER) ? TASKS * N1 : 1];
+    constexpr bool kManakov = (MODE == TM_FIRST || MODE == TM_ITER || MODE == TM_ITERF || MODE == TM_ROT);
+    constexpr bool kSums = (MODE == TM_ITER || MODE == TM_ITERF);
+    __shared__ float pbuf[kManakov ? TASKS * N1 : 1];
 
     const int tid = threadIdx.x, grp = tid / Q1, t = tid % Q1;
     const int task = blockIdx.x * TASKS + grp;
@@ -78,13 +88,13 @@ k_time(const TimeArgs A) {
 
     // Secondary streams of the pointwise stage: start their HBM->L2 fetch now so that it overlaps the
     // W-row load and the inverse transform (one 128-byte line per lane and trip).
-    if constexpr (MODE == TM_FIRST || MODE == TM_ITER) {
+    if constexpr (kManakov) {
         constexpr int LINES = N1 * 8 / 128;
         for (int l = t; l < LINES; l += Q1) {
             prefetch_l2(reinterpret_cast<const char*>(A.aux0 + base) + l * 128);
-            if constexpr (MODE == TM_ITER) prefetch_l2(reinterpret_cast<const char*>(A.ehd + base) + l * 128);
+            if constexpr (MODE == TM_ITER || MODE == TM_ROT) prefetch_l2(reinterpret_cast<const char*>(A.ehd + base) + l * 128);
         }
-        if constexpr (MODE == TM_ITER) {
+        if constexpr (MODE == TM_ITER || MODE == TM_ROT) {
             if (pol == 0)
                 for (int l = t; l < LINES / 2; l += Q1)
                     prefetch_l2(reinterpret_cast<const char*>(A.pch + (int64_t)row * N1) + l * 128);
@@ -95,7 +105,8 @@ k_time(const TimeArgs A) {
     // written by the preceding kernel of the stream (programmatic dependent launch).
     pdl_wait();
     pdl_launch_dependents();
-    if constexpr (MODE == TM_ITER) {
+    if (A.need_flag && *reinterpret_cast<const volatile long long*>(A.need_flag) != A.need_id) return;
+    if constexpr (kSums) {
         // speculative launch of an iteration whose predecessor already converged: nothing to do
         if (A.ext.mail && *reinterpret_cast<volatile long long*>(A.ext.converged_step) == A.ext.step_id) return;
     }
@@ -105,7 +116,7 @@ k_time(const TimeArgs A) {
         const float2* src = A.in + base;
 #pragma unroll
         for (int a = 0; a < 32; ++a) v[a] = ld_stream(src + Q1 * a + t);
-    } else {
+    } else if constexpr (MODE != TM_ROT) {
         const float2* src = A.in + base;
 #pragma unroll
         for (int s = 0; s < 32; ++s) v[s] = ld_stream(src + s * Q1 + t);
@@ -133,7 +144,7 @@ k_time(const TimeArgs A) {
 #pragma unroll
         for (int a = 0; a < 32; ++a) v[a] = cmul(v[a], phase_rot(A.cphi * cabs2(v[a])));
     }
-    if constexpr (MODE == TM_FIRST || MODE == TM_ITER) {
+    if constexpr (kManakov) {
         static_assert(NP == 2, "Manakov modes need both polarisations in the CTA");
         float* pown = pbuf + grp * N1;
         const float* poth = pbuf + (grp ^ 1) * N1;  // the other polarisation of the same row
@@ -146,30 +157,35 @@ k_time(const TimeArgs A) {
                 st_stream(ehd_out + Q1 * a + t, v[a]);
                 pown[Q1 * a + t] = cabs2(ld_stream(ech + Q1 * a + t));
             }
+        } else if constexpr (MODE == TM_ROT) {
+            const float2* ec = A.aux0 + base;  // the iterate stored by TM_ITERF
+#pragma unroll
+            for (int a = 0; a < 32; ++a) pown[Q1 * a + t] = cabs2(ld_stream(ec + Q1 * a + t));
         } else {
             // v = E_fd: convergence sums against the previous iterate, store as the new iterate.  aux0 and
             // aux1 may be the SAME buffer (in-place update keeps the working set L2-sized): every thread
             // reads its own samples before it overwrites them; two batches of 16 keep the loads in flight.
             const float2* ec = A.aux0 + base;
             float2* ec_new = A.aux1 + base;
+            constexpr int EB = (MODE == TM_ITERF) ? 8 : 16;  // TM_ITERF keeps v[] live: smaller batches
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-                float2 e[16];
+            for (int hb = 0; hb < 32 / EB; ++hb) {
+                float2 e[EB];
 #pragma unroll
-                for (int a = 0; a < 16; ++a) e[a] = ld_stream_ordered(ec + Q1 * (16 * hb + a) + t);
+                for (int a = 0; a < EB; ++a) e[a] = ld_stream_ordered(ec + Q1 * (EB * hb + a) + t);
 #pragma unroll
-                for (int a = 0; a < 16; ++a) {
-                    const int aa = 16 * hb + a;
+                for (int a = 0; a < EB; ++a) {
+                    const int aa = EB * hb + a;
                     s_num += cabs2(make_float2(v[aa].x - e[a].x, v[aa].y - e[a].y));  // channels.py:517
                     s_den += cabs2(e[a]);
                     st_stream(ec_new + Q1 * aa + t, v[aa]);
-                    pown[Q1 * aa + t] = cabs2(v[aa]);
+                    if constexpr (MODE == TM_ITER) pown[Q1 * aa + t] = cabs2(v[aa]);
                 }
             }
         }
         float* pch = A.pch + (int64_t)row * N1;
-        float pc[MODE == TM_ITER ? 32 : 1];
-        if constexpr (MODE == TM_ITER) {
+        float pc[(MODE == TM_ITER || MODE == TM_ROT) ? 32 : 1];
+        if constexpr (MODE == TM_ITER || MODE == TM_ROT) {
             // E_fd has been stored, so v[] is free: fetch the whole E_hd and P_ch rows in one batch (64
             // loads in flight per thread) before the barrier.  The rotation loop below contains a branch
             // (large-phase path), which would otherwise make every trip wait for its own two loads.
@@ -179,9 +195,11 @@ k_time(const TimeArgs A) {
 #pragma unroll
             for (int a = 0; a < 32; ++a) pc[a] = ld_stream_pinned(pch + Q1 * a + t);
         }
-        __syncthreads();
+        // TM_ITERF: v stays E_fd, the field the next step starts from.  (It runs in fixed-step mode only, where
+        // the maximum power — used for the adaptive step size, channels.py:392-397 — is not needed.)
+        if constexpr (MODE != TM_ITERF) __syncthreads();
 #pragma unroll
-        for (int a = 0; a < 32; ++a) {
+        for (int a = 0; a < (MODE == TM_ITERF ? 0 : 32); ++a) {
             const float P = pown[Q1 * a + t] + poth[Q1 * a + t];
             float ph;
             if constexpr (MODE == TM_FIRST) {
@@ -193,6 +211,14 @@ k_time(const TimeArgs A) {
             }
             v[a] = cmul(v[a], phase_rot(ph));  // channels.py:414-417
         }
+    }
+
+    // The convergence sums are final here: post them now, so that the ticket's fence + atomic round trip
+    // overlaps the forward transform and the stores below.
+    unsigned my_ticket = 0;
+    if constexpr (kSums) {
+        if (pol == 1) s_max = 0.f;  // both polarisation tasks saw the same total power
+        my_ticket = block_reduce3_post(s_num, s_den, s_max, A.partials, A.ticket);
     }
 
     // ---- leave: forward FFT over n1 + inter-pass twiddle -> W row ---------------------------------------
@@ -208,10 +234,7 @@ k_time(const TimeArgs A) {
             });
         });
     }
-    if constexpr (MODE == TM_ITER) {
-        if (pol == 1) s_max = 0.f;  // both polarisation tasks saw the same total power
-        block_reduce3_finalize(s_num, s_den, s_max, A.partials, A.sums, A.ticket, &A.ext);
-    }
+    if constexpr (kSums) block_reduce3_final(my_ticket, A.partials, A.sums, A.ticket, &A.ext);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -223,13 +246,19 @@ k_time(const TimeArgs A) {
 template <int Q2, int C>
 __global__ void __launch_bounds__(Q2* C, (Q2 * C <= 256) ? 2 : 1)
 k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __restrict__ tw, int N1,
-       const long long* __restrict__ converged_step, long long step_id) {
+       const long long* __restrict__ converged_step, long long step_id,
+       const long long* __restrict__ need_flag, long long need_id) {
     using namespace fft;
     constexpr int STR = Q2 * C + C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xr = reinterpret_cast<float*>(smem_raw);  // [32*STR]
     float* xi = xr + 32 * STR;
+    // twiddle table (both orientations, 2 x 32*Q2 entries) staged in shared memory: 63 table reads per
+    // thread sit inside the dependent transform chains, and a shared-memory read is both faster than an
+    // L1 hit and immune to eviction by the streamed field data
+    float2* tws = reinterpret_cast<float2*>(xi + 32 * STR);
     const int tid = threadIdx.x, q = tid / C, c = tid % C;
+    for (int i = tid; i < 2 * 32 * Q2; i += Q2 * C) tws[i] = __ldg(tw + i);
     const int tiles_per_pol = N1 / C;
     const int pol = blockIdx.x / tiles_per_pol, tile = blockIdx.x % tiles_per_pol;
     float2* base = W + ((int64_t)pol * (32 * Q2)) * N1 + tile * C + c;  // row n2 = 0 of this column
@@ -246,14 +275,31 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
     pdl_wait();  // W was written by the preceding time pass (programmatic dependent launch)
     pdl_launch_dependents();
     if (converged_step && *reinterpret_cast<const volatile long long*>(converged_step) == step_id) return;
+    if (need_flag && *reinterpret_cast<const volatile long long*>(need_flag) != need_id) return;
     float2 v[32];
 #pragma unroll
     for (int a = 0; a < 32; ++a) v[a] = ld_stream(base + (int64_t)(Q2 * a + q) * N1);
-    coop_fft_forward<Q2, C, C>(v, xr, xi, tw, q, c, bsync);
+    __syncthreads();  // twiddle table staged
+    coop_fft_forward<Q2, C, C>(v, xr, xi, tws, q, c, bsync);
+    {
+        // operator slice: groups of 8 loads, the next group in flight while the current one is applied
+        float2 l0[8], l1[8];
 #pragma unroll
-    for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], ld_stream(lp + s * (Q2 * C)));
+        for (int s = 0; s < 8; ++s) l0[s] = ld_stream_pinned(lp + s * (Q2 * C));
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (g < 3) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s) l1[s] = ld_stream_pinned(lp + (8 * (g + 1) + s) * (Q2 * C));
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s) v[8 * g + s] = cmul(v[8 * g + s], l0[s]);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) l0[s] = l1[s];
+        }
+    }
     __syncthreads();
-    coop_fft_inverse<Q2, C, C>(v, xr, xi, tw, q, c, bsync);
+    coop_fft_inverse<Q2, C, C>(v, xr, xi, tws, q, c, bsync);
 #pragma unroll
     for (int a = 0; a < 32; ++a) st_stream(base + (int64_t)(Q2 * a + q) * N1, v[a]);
 }

@@ -56,6 +56,7 @@ struct ocb_ssfm_plan {
     Mail* h_mail = nullptr;   // host view
     Mail* d_mail = nullptr;   // device view of the same memory
     long long* conv_flag = nullptr;  // device: id of the last step whose loop converged
+    long long* final_flag = nullptr; // device: id of the last step whose predicted-last iteration (TM_ITERF) converged
     unsigned long long mail_seq = 0;
     long long step_counter = 0;
     // staging for the _host variants
@@ -180,7 +181,7 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
     p->T2 = (float2*)c; c += align_up(p->N * (int64_t)sizeof(float2), 256);
     p->Pch = (float*)c; c += align_up(((int64_t)(p->rows + 1) / 2) * p->N * sizeof(float), 256);
     p->partials = (double*)c; c += align_up((int64_t)p->max_blocks * 3 * sizeof(double), 256);
-    p->sums = (double*)c; p->ticket = (unsigned*)(c + 64); p->conv_flag = (long long*)(c + 128); c += 256;
+    p->sums = (double*)c; p->ticket = (unsigned*)(c + 64); p->conv_flag = (long long*)(c + 128); p->final_flag = (long long*)(c + 192); c += 256;
     p->fft_area = c; c += align_up((int64_t)p->fft_work, 256);
     if (p->fft_work > 0) OCB_CUFFT(cufftSetWorkArea(p->fft, p->fft_area));
     if (p->fused_ok) {

@@ -70,22 +70,26 @@ struct FinalizeExt {
     long long step_id;
     unsigned long long seq;
     double tol;
+    long long* final_step;      // TM_ITERF only: set to step_id when the predicted-last iteration did converge
 };
 
+// The reduction is split in two so that a kernel can POST its partial sums as soon as they are final and
+// only later — after the rest of its work — ask whether it was the last block: the fence + atomic round
+// trip of the ticket then overlaps that work instead of extending every block's lifetime.
+//   post : block-level sums -> partials[blockIdx.x]; thread 0 takes a ticket (its value is meaningful in thread 0)
+//   final: the block that drew the last ticket adds up all partials in a fixed order, publishes them and,
+//          with `ext`, the decision lim < tol (channels.py:517-519, 429) + the host mail
 template <typename TS>  // float: one row per thread ; double: persistent kernels that sum several rows per thread
-__device__ __forceinline__ void block_reduce3_finalize(TS s0, TS s1, float m,
-                                                       double* __restrict__ partials,
-                                                       double* __restrict__ out,
-                                                       unsigned* __restrict__ ticket,
-                                                       const FinalizeExt* ext = nullptr) {
+__device__ __forceinline__ unsigned block_reduce3_post(TS s0, TS s1, float m, double* __restrict__ partials,
+                                                       unsigned* __restrict__ ticket) {
     __shared__ double sh0[32], sh1[32], sh2[32];
-    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     // warp level in the caller's type (float: <= 32 addends), block level in double
     TS w0 = warp_sum(s0), w1 = warp_sum(s1);
     float wm = warp_max(m);
     if (lane == 0) { sh0[wid] = (double)w0; sh1[wid] = (double)w1; sh2[wid] = (double)wm; }
     __syncthreads();
+    unsigned t = 0;
     if (wid == 0) {
         double a = lane < nw ? sh0[lane] : 0.0, b = lane < nw ? sh1[lane] : 0.0;
         double c = lane < nw ? sh2[lane] : 0.0;
@@ -97,10 +101,18 @@ __device__ __forceinline__ void block_reduce3_finalize(TS s0, TS s1, float m,
             partials[3 * blockIdx.x + 1] = b;
             partials[3 * blockIdx.x + 2] = c;
             __threadfence();
-            unsigned t = atomicAdd(ticket, 1u);
-            is_last = (t == gridDim.x - 1);
+            t = atomicAdd(ticket, 1u);
         }
     }
+    return t;
+}
+__device__ __forceinline__ void block_reduce3_final(unsigned my_ticket, double* __restrict__ partials,
+                                                    double* __restrict__ out, unsigned* __restrict__ ticket,
+                                                    const FinalizeExt* ext = nullptr) {
+    __shared__ double sh0[32], sh1[32], sh2[32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (threadIdx.x == 0) is_last = (my_ticket == gridDim.x - 1);
     __syncthreads();
     if (!is_last) return;
     __threadfence();
@@ -114,7 +126,6 @@ __device__ __forceinline__ void block_reduce3_finalize(TS s0, TS s1, float m,
     a = warp_sum(a); b = warp_sum(b);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
-    __syncthreads();
     if (lane == 0) { sh0[wid] = a; sh1[wid] = b; sh2[wid] = c; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -124,7 +135,10 @@ __device__ __forceinline__ void block_reduce3_finalize(TS s0, TS s1, float m,
         *ticket = 0u;  // ready for the next launch
         if (ext && ext->mail) {
             const int conv = (sqrt(ta) / sqrt(tb) < ext->tol) ? 1 : 0;  // channels.py:517-519, 429
-            if (conv) *ext->converged_step = ext->step_id;
+            if (conv) {
+                *ext->converged_step = ext->step_id;
+                if (ext->final_step) *ext->final_step = ext->step_id;
+            }
             volatile Mail* mb = ext->mail + (ext->seq % kMailSlots);
             mb->sums[0] = ta; mb->sums[1] = tb; mb->sums[2] = tc;
             mb->converged = conv;
@@ -132,6 +146,13 @@ __device__ __forceinline__ void block_reduce3_finalize(TS s0, TS s1, float m,
             mb->seq = ext->seq;
         }
     }
+}
+template <typename TS>
+__device__ __forceinline__ void block_reduce3_finalize(TS s0, TS s1, float m, double* __restrict__ partials,
+                                                       double* __restrict__ out, unsigned* __restrict__ ticket,
+                                                       const FinalizeExt* ext = nullptr) {
+    const unsigned t = block_reduce3_post(s0, s1, m, partials, ticket);
+    block_reduce3_final(t, partials, out, ticket, ext);
 }
 
 // phase rotation exp(j ph): short polynomial for the small per-step phases (|ph| < 0.5 rad,
