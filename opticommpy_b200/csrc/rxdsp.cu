@@ -456,6 +456,8 @@ int launch_mimo(bool wl, cudaStream_t st, const float2* X, const float2* REF, fl
     return 0;
 }
 
+#include "rxdsp_eq_la.cuh"
+
 }  // namespace
 
 extern "C" int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hwl, void* y, void* errSq,
@@ -488,6 +490,19 @@ extern "C" int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hw
         if ((v == 8 || v == 16 || v == 32) && (nTaps + v - 1) / v <= 4 && (v == 32 || (nTaps + v - 1) / v >= (v == 16 ? 2 : 1))) lps = v;
     }
     const int tpl = (nTaps + lps - 1) / lps;
+    // latency mode (a warp per task): look-ahead kernel, rxdsp_eq_la.cuh (OCB_EQ_LA=0: plain recurrence, for A/B runs)
+    static const bool use_la = !(getenv("OCB_EQ_LA") && atoi(getenv("OCB_EQ_LA")) == 0);
+#define OCB_MIMO_LA_CASE(NM_, TPL_)                                                                            \
+    if (use_la && lps == 32 && nModes == NM_ && tpl == TPL_)                                                   \
+        return launch_mimo_la<NM_, TPL_>(runWL != 0, st, (const float2*)x, (const float2*)ref, (float2*)H,     \
+                                         (float2*)Hwl, (float2*)y, (float*)errSq, (float2*)Hiter, nStreams,    \
+                                         x_stream_stride, ref_stream_stride, y_stream_stride,                  \
+                                         err_stream_stride, err_mode_stride, L, nTaps, SpS, alg, mu,           \
+                                         (const float2*)constSymb, M, (const float*)radii, nR, Rcma);
+    OCB_MIMO_LA_CASE(1, 1) OCB_MIMO_LA_CASE(1, 2) OCB_MIMO_LA_CASE(1, 3) OCB_MIMO_LA_CASE(1, 4)
+    OCB_MIMO_LA_CASE(2, 1) OCB_MIMO_LA_CASE(2, 2) OCB_MIMO_LA_CASE(2, 3) OCB_MIMO_LA_CASE(2, 4)
+    OCB_MIMO_LA_CASE(4, 1) OCB_MIMO_LA_CASE(4, 2)
+#undef OCB_MIMO_LA_CASE
 #define OCB_MIMO_CASE(NM_, TPL_, LPS_)                                                                         \
     if (nModes == NM_ && lps == LPS_ && tpl == TPL_)                                                           \
         return launch_mimo<NM_, TPL_, LPS_>(runWL != 0, st, (const float2*)x, (const float2*)ref,              \
