@@ -167,7 +167,7 @@ k_time(const TimeArgs A) {
             // reads its own samples before it overwrites them; two batches of 16 keep the loads in flight.
             const float2* ec = A.aux0 + base;
             float2* ec_new = A.aux1 + base;
-            constexpr int EB = (MODE == TM_ITERF) ? 8 : 16;  // TM_ITERF keeps v[] live: smaller batches
+            constexpr int EB = 16;
 #pragma unroll
             for (int hb = 0; hb < 32 / EB; ++hb) {
                 float2 e[EB];
@@ -216,13 +216,16 @@ k_time(const TimeArgs A) {
     // The convergence sums are final here: post them now, so that the ticket's fence + atomic round trip
     // overlaps the forward transform and the stores below.
     unsigned my_ticket = 0;
-    if constexpr (kSums) {
+    if constexpr (MODE == TM_ITER) {
         if (pol == 1) s_max = 0.f;  // both polarisation tasks saw the same total power
         my_ticket = block_reduce3_post(s_num, s_den, s_max, A.partials, A.ticket);
     }
 
     // ---- leave: forward FFT over n1 + inter-pass twiddle -> W row ---------------------------------------
     coop_fft_forward<Q1, 1, 1>(v, xr, xi, tw, t, 0, wsync);
+    // TM_ITERF has just issued its 32 stores of the new iterate: post after the transform, when they have
+    // drained, so that the ticket's fence does not wait for them
+    if constexpr (MODE == TM_ITERF) my_ticket = block_reduce3_post(s_num, s_den, 0.f, A.partials, A.ticket);
     {
         float2* dst = A.out + base;
         static_for<0, G>([&](auto gg) {
