@@ -83,6 +83,12 @@ int ocb_ssfm_plan_engine(const ocb_ssfm_plan* plan); /* engine a run would use n
  * (fft + multiply + ifft).  profile_read: out6[2k] = summed ms, out6[2k+1] = launches, then reset. */
 int ocb_ssfm_plan_profile(ocb_ssfm_plan* plan, int enable);
 int ocb_ssfm_plan_profile_read(ocb_ssfm_plan* plan, double* out6);
+/* Tuning/measurement aid (no reference counterpart): launch one pass kernel of the fused engine `reps` times
+ * back to back on the plan's own (L2-resident) buffers, exactly as the step loop launches it, and return the
+ * average duration in microseconds (CUDA events on `stream`).  which: 0 = frequency pass (k_freq),
+ * 1 = first time pass (TM_FIRST), 2 = iteration time pass (TM_ITER), 3 = predicted-last iteration (TM_ITERF),
+ * 4 = forward time pass (TM_FWD).  The field buffers hold garbage afterwards.                          */
+int ocb_ssfm_plan_pass_time(ocb_ssfm_plan* plan, int which, int reps, double* avg_us, void* stream);
 
 /* ---- layout conversion ---------------------------------------------------------------
  * (N, C) interleaved-column host/device array <-> planar rows[C][N] complex64.

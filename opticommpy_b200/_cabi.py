@@ -66,6 +66,7 @@ SIGNATURES = {
     "ocb_ssfm_plan_engine": (_i, [_vp]),
     "ocb_ssfm_plan_profile": (_i, [_vp, _i]),
     "ocb_ssfm_plan_profile_read": (_i, [_vp, C.POINTER(C.c_double)]),
+    "ocb_ssfm_plan_pass_time": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _vp]),
     "ocb_pack_fields": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp]),
     "ocb_unpack_fields": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),
     "ocb_cast_complex": (_i, [_vp, _i, _vp, _i, _i64, _vp]),

@@ -119,54 +119,104 @@ struct Coop {
     static constexpr int G = 32 / Q;
 };
 
-template <int Q, int CP, int PAD, typename SyncF>
+// HALF = true: the exchange runs in two rounds (real parts, then imaginary parts) through ONE planar array
+// (xr; xi unused), which halves the shared-memory footprint at the price of two more barriers per transform.
+template <int Q, int CP, int PAD, bool HALF = false, typename SyncF>
 __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi, const float2* __restrict__ tw,
                                                  int q, int c, SyncF&& sync) {
     constexpr int G = 32 / Q, STR = Q * CP + PAD;
     fft_dif<32, -1>(v);  // v[brev5(ka)] = Z[ka]
-    static_for<0, 32>([&](auto kk) {
-        constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
-        float2 z = v[SLOT];
-        if constexpr (KA != 0) z = cmul(z, tw[KA * Q + q]);
-        xr[KA * STR + q * CP + c] = z.x;
-        xi[KA * STR + q * CP + c] = z.y;
-    });
-    sync();
-    // thread t = q now gathers ka = t*G + g, all j: u[g*Q + j] = Z[ka][j]
-    static_for<0, G>([&](auto gg) {
-        constexpr int GI = decltype(gg)::value;
-        const int ka = q * G + GI;
-        static_for<0, Q>([&](auto jj) {
-            constexpr int J = decltype(jj)::value;
-            v[GI * Q + J] = make_float2(xr[ka * STR + J * CP + c], xi[ka * STR + J * CP + c]);
+    if constexpr (!HALF) {
+        static_for<0, 32>([&](auto kk) {
+            constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
+            float2 z = v[SLOT];
+            if constexpr (KA != 0) z = cmul(z, tw[KA * Q + q]);
+            xr[KA * STR + q * CP + c] = z.x;
+            xi[KA * STR + q * CP + c] = z.y;
         });
-    });
+        sync();
+        // thread t = q now gathers ka = t*G + g, all j: u[g*Q + j] = Z[ka][j]
+        static_for<0, G>([&](auto gg) {
+            constexpr int GI = decltype(gg)::value;
+            const int ka = q * G + GI;
+            static_for<0, Q>([&](auto jj) {
+                constexpr int J = decltype(jj)::value;
+                v[GI * Q + J] = make_float2(xr[ka * STR + J * CP + c], xi[ka * STR + J * CP + c]);
+            });
+        });
+    } else {
+        static_for<0, 32>([&](auto kk) {
+            constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
+            if constexpr (KA != 0) v[SLOT] = cmul(v[SLOT], tw[KA * Q + q]);
+            xr[KA * STR + q * CP + c] = v[SLOT].x;
+        });
+        sync();
+        float re[32];
+        static_for<0, G>([&](auto gg) {
+            constexpr int GI = decltype(gg)::value;
+            const int ka = q * G + GI;
+            static_for<0, Q>([&](auto jj) { constexpr int J = decltype(jj)::value; re[GI * Q + J] = xr[ka * STR + J * CP + c]; });
+        });
+        sync();
+        static_for<0, 32>([&](auto kk) {
+            constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
+            xr[KA * STR + q * CP + c] = v[SLOT].y;
+        });
+        sync();
+        static_for<0, G>([&](auto gg) {
+            constexpr int GI = decltype(gg)::value;
+            const int ka = q * G + GI;
+            static_for<0, Q>([&](auto jj) {
+                constexpr int J = decltype(jj)::value;
+                v[GI * Q + J] = make_float2(re[GI * Q + J], xr[ka * STR + J * CP + c]);
+            });
+        });
+    }
     static_for<0, G>([&](auto gg) { fft_dif<Q, -1>(v + decltype(gg)::value * Q); });
 }
 
-template <int Q, int CP, int PAD, typename SyncF>
+// twt: the transposed copy of the table, entry [J][ka] (defaults to tw + 32*Q; for Q = 32 the table is
+// symmetric and twt may alias tw).
+template <int Q, int CP, int PAD, bool HALF = false, typename SyncF>
 __device__ __forceinline__ void coop_fft_inverse(float2* v, float* xr, float* xi, const float2* __restrict__ tw,
-                                                 int q, int c, SyncF&& sync) {
+                                                 int q, int c, SyncF&& sync, const float2* __restrict__ twt = nullptr) {
     constexpr int G = 32 / Q, STR = Q * CP + PAD;
+    if (twt == nullptr) twt = tw + 32 * Q;
     static_for<0, G>([&](auto gg) { fft_dit<Q, +1>(v + decltype(gg)::value * Q); });  // over kq -> q'
     static_for<0, G>([&](auto gg) {
         constexpr int GI = decltype(gg)::value;
         const int ka = q * G + GI;
         static_for<0, Q>([&](auto jj) {
             constexpr int J = decltype(jj)::value;  // q'
-            float2 z = v[GI * Q + J];
-            // transposed copy of the table (tw + 32*Q): entry [J][ka], so that lanes (ka) are contiguous
-            const float2 w = tw[32 * Q + J * 32 + ka];
-            z = cmul_conj(z, w);  // conj twiddle for the inverse
+            // transposed copy of the table: entry [J][ka], so that lanes (ka) are contiguous
+            const float2 w = twt[J * 32 + ka];
+            const float2 z = cmul_conj(v[GI * Q + J], w);  // conj twiddle for the inverse
+            v[GI * Q + J] = z;
             xr[ka * STR + J * CP + c] = z.x;
-            xi[ka * STR + J * CP + c] = z.y;
+            if constexpr (!HALF) xi[ka * STR + J * CP + c] = z.y;
         });
     });
     sync();
-    static_for<0, 32>([&](auto kk) {
-        constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
-        v[SLOT] = make_float2(xr[KA * STR + q * CP + c], xi[KA * STR + q * CP + c]);
-    });
+    if constexpr (!HALF) {
+        static_for<0, 32>([&](auto kk) {
+            constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
+            v[SLOT] = make_float2(xr[KA * STR + q * CP + c], xi[KA * STR + q * CP + c]);
+        });
+    } else {
+        float re[32];
+        static_for<0, 32>([&](auto kk) { constexpr int KA = decltype(kk)::value; re[KA] = xr[KA * STR + q * CP + c]; });
+        sync();
+        static_for<0, G>([&](auto gg) {
+            constexpr int GI = decltype(gg)::value;
+            const int ka = q * G + GI;
+            static_for<0, Q>([&](auto jj) { constexpr int J = decltype(jj)::value; xr[ka * STR + J * CP + c] = v[GI * Q + J].y; });
+        });
+        sync();
+        static_for<0, 32>([&](auto kk) {
+            constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
+            v[SLOT] = make_float2(re[KA], xr[KA * STR + q * CP + c]);
+        });
+    }
     fft_dit<32, +1>(v);  // natural a'
 }
 

@@ -31,7 +31,7 @@ int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP,
                   long long step_id, const long long* need_flag, long long need_id, cudaStream_t st) {
     static bool configured = false;
     constexpr int C = kFreqC;
-    const size_t smem = (size_t)2 * 32 * (Q2 * C + C) * sizeof(float) + (size_t)2 * 32 * Q2 * sizeof(float2);
+    const size_t smem = FreqCfg<Q2, C>::SMEM_BYTES;
     if (!configured) {
         OCB_CUDA(cudaFuncSetAttribute(k_freq<Q2, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -406,5 +406,41 @@ static int fused_nlse_run(ocb_ssfm_plan* p, void* row_inout, const ocb_nlse_para
         }
     }
     if (launch_transpose(p, E, (float2*)row_inout, 1, false, 1.0f, st)) return 1;
+    return 0;
+}
+
+// Measurement aid: see include/opticomm_b200.h (ocb_ssfm_plan_pass_time)
+extern "C" int ocb_ssfm_plan_pass_time(ocb_ssfm_plan* p, int which, int reps, double* avg_us, void* stream) {
+    OCB_REQUIRE(p && avg_us && reps > 0, "pass_time: bad argument");
+    OCB_REQUIRE(p->ws != nullptr && p->fused_ok && p->rows == 2, "pass_time: needs a bound dual-pol plan of the fused engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fused_init_tables(p, st)) return 1;
+    const int N1 = 32 * p->q1;
+    if (launch_linop_perm(p, p->T1, 0.0, 0.0, 1.0, 1.0, 1.0 / (double)p->N, st)) return 1;  // unit operator
+    cudaEvent_t e0, e1;
+    OCB_CUDA(cudaEventCreate(&e0));
+    OCB_CUDA(cudaEventCreate(&e1));
+    auto one = [&]() -> int {
+        TimeArgs a = time_base(p);
+        a.in = p->G; a.out = p->G; a.aux0 = p->A; a.aux1 = p->A; a.ehd = p->Ehd; a.pch = p->Pch; a.cphi = 1e-3f;
+        switch (which) {
+            case 0: return launch_freq(p->q2, p->G, p->T1, p->tw2, N1, 2, st);
+            case 1: a.aux1 = p->Ehd; return launch_time<2, TM_FIRST>(p->q1, a, st);
+            case 2: return launch_time<2, TM_ITER>(p->q1, a, st);
+            case 3: return launch_time<2, TM_ITERF>(p->q1, a, st);
+            case 4: a.in = p->A; return launch_time<2, TM_FWD>(p->q1, a, st);
+        }
+        return fail("pass_time: unknown pass", __FILE__, __LINE__);
+    };
+    for (int i = 0; i < 3; ++i) if (one()) return 1;  // warm-up
+    OCB_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < reps; ++i) if (one()) return 1;
+    OCB_CUDA(cudaEventRecord(e1, st));
+    OCB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    OCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *avg_us = 1e3 * (double)ms / reps;
     return 0;
 }

@@ -152,10 +152,17 @@ k_time(const TimeArgs A) {
             // v = E_hd (store it); power of the step-start field Ech  (channels.py:388)
             float2* ehd_out = A.aux1 + base;
             const float2* ech = A.aux0 + base;
+            // two batches of 16 loads, each issued together ahead of the stores that would otherwise pace them
 #pragma unroll
-            for (int a = 0; a < 32; ++a) {
-                st_stream(ehd_out + Q1 * a + t, v[a]);
-                pown[Q1 * a + t] = cabs2(ld_stream(ech + Q1 * a + t));
+            for (int hb = 0; hb < 2; ++hb) {
+                float2 e[16];
+#pragma unroll
+                for (int a = 0; a < 16; ++a) e[a] = ld_stream_pinned(ech + Q1 * (16 * hb + a) + t);
+#pragma unroll
+                for (int a = 0; a < 16; ++a) {
+                    st_stream(ehd_out + Q1 * (16 * hb + a) + t, v[16 * hb + a]);
+                    pown[Q1 * (16 * hb + a) + t] = cabs2(e[a]);
+                }
             }
         } else if constexpr (MODE == TM_ROT) {
             const float2* ec = A.aux0 + base;  // the iterate stored by TM_ITERF
@@ -246,63 +253,67 @@ k_time(const TimeArgs A) {
 // p0 + c; a warp touches 32/C rows x C*8 contiguous bytes per access.
 // LP is stored in consumption order: LP[((tile*32 + slot)*Q2 + q)*C + c], see k_tab_linop_perm.
 // ------------------------------------------------------------------------------------------
+// Shared memory of one k_freq CTA: the (half-footprint) exchange array, the twiddle table(s) and the tile's
+// whole operator slice, which is fetched by cp.async BEFORE the kernel waits for its predecessor.
+template <int Q2, int C>
+struct FreqCfg {
+    static constexpr int STR = Q2 * C + C;
+    static constexpr int TW_ENTRIES = (Q2 == 32 ? 1 : 2) * 32 * Q2;  // a 32 x 32 table is symmetric: one copy
+    static constexpr int LP_ENTRIES = 32 * Q2 * C;
+    static constexpr int SMEM_BYTES = 32 * STR * 4 + TW_ENTRIES * 8 + LP_ENTRIES * 8;
+};
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
 template <int Q2, int C>
 __global__ void __launch_bounds__(Q2* C, (Q2 * C <= 256) ? 2 : 1)
 k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __restrict__ tw, int N1,
        const long long* __restrict__ converged_step, long long step_id,
        const long long* __restrict__ need_flag, long long need_id) {
     using namespace fft;
-    constexpr int STR = Q2 * C + C;
+    using Cfg = FreqCfg<Q2, C>;
+    constexpr int STR = Cfg::STR, NT = Q2 * C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* xr = reinterpret_cast<float*>(smem_raw);  // [32*STR]
-    float* xi = xr + 32 * STR;
-    // twiddle table (both orientations, 2 x 32*Q2 entries) staged in shared memory: 63 table reads per
-    // thread sit inside the dependent transform chains, and a shared-memory read is both faster than an
-    // L1 hit and immune to eviction by the streamed field data
-    float2* tws = reinterpret_cast<float2*>(xi + 32 * STR);
+    float* xr = reinterpret_cast<float*>(smem_raw);  // [32*STR] real parts, then imaginary parts (two rounds)
+    // twiddle table staged in shared memory: 63 table reads per thread sit inside the dependent transform
+    // chains, and a shared-memory read is both faster than an L1 hit and immune to eviction by the field data
+    float2* tws = reinterpret_cast<float2*>(xr + 32 * STR);
+    float2* lps = tws + Cfg::TW_ENTRIES;             // operator slice of this tile, consumption order
     const int tid = threadIdx.x, q = tid / C, c = tid % C;
-    for (int i = tid; i < 2 * 32 * Q2; i += Q2 * C) tws[i] = __ldg(tw + i);
     const int tiles_per_pol = N1 / C;
     const int pol = blockIdx.x / tiles_per_pol, tile = blockIdx.x % tiles_per_pol;
     float2* base = W + ((int64_t)pol * (32 * Q2)) * N1 + tile * C + c;  // row n2 = 0 of this column
-    const float2* lp = LP + (int64_t)tile * 32 * (Q2 * C) + q * C + c;
     auto bsync = [] { __syncthreads(); };
 
-    // the tile's slice of the operator table (32 x Q2*C entries) is needed after the forward transform:
-    // start its HBM->L2 fetch now (one 128-byte line per thread and trip)
+    // Neither the operator table nor the twiddle table depends on the preceding kernel: fetch them now, so that
+    // the copies overlap the predecessor's tail (programmatic dependent launch) and this kernel's own W loads.
     {
-        const char* lp_tile = reinterpret_cast<const char*>(LP + (int64_t)tile * 32 * (Q2 * C));
-        constexpr int LINES = 32 * Q2 * C * 8 / 128;
-        for (int l = tid; l < LINES; l += Q2 * C) prefetch_l2(lp_tile + l * 128);
+        const char* src = reinterpret_cast<const char*>(LP + (int64_t)tile * Cfg::LP_ENTRIES);
+        char* dst = reinterpret_cast<char*>(lps);
+        for (int i = tid; i < Cfg::LP_ENTRIES * 8 / 16; i += NT) cp_async16_cg(dst + i * 16, src + i * 16);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    for (int i = tid; i < Cfg::TW_ENTRIES; i += NT) tws[i] = __ldg(tw + i);
+    const float2* twt = (Q2 == 32) ? tws : tws + 32 * Q2;
+
     pdl_wait();  // W was written by the preceding time pass (programmatic dependent launch)
     pdl_launch_dependents();
-    if (converged_step && *reinterpret_cast<const volatile long long*>(converged_step) == step_id) return;
-    if (need_flag && *reinterpret_cast<const volatile long long*>(need_flag) != need_id) return;
+    if ((converged_step && *reinterpret_cast<const volatile long long*>(converged_step) == step_id) ||
+        (need_flag && *reinterpret_cast<const volatile long long*>(need_flag) != need_id)) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
     float2 v[32];
 #pragma unroll
     for (int a = 0; a < 32; ++a) v[a] = ld_stream(base + (int64_t)(Q2 * a + q) * N1);
-    __syncthreads();  // twiddle table staged
-    coop_fft_forward<Q2, C, C>(v, xr, xi, tws, q, c, bsync);
-    {
-        // operator slice: groups of 8 loads, the next group in flight while the current one is applied
-        float2 l0[8], l1[8];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // twiddle table and operator slice staged
+    coop_fft_forward<Q2, C, C, true>(v, xr, nullptr, tws, q, c, bsync);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) l0[s] = ld_stream_pinned(lp + s * (Q2 * C));
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            if (g < 3) {
-#pragma unroll
-                for (int s = 0; s < 8; ++s) l1[s] = ld_stream_pinned(lp + (8 * (g + 1) + s) * (Q2 * C));
-            }
-#pragma unroll
-            for (int s = 0; s < 8; ++s) v[8 * g + s] = cmul(v[8 * g + s], l0[s]);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) l0[s] = l1[s];
-        }
-    }
+    for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], lps[s * NT + tid]);
     __syncthreads();
-    coop_fft_inverse<Q2, C, C>(v, xr, xi, tws, q, c, bsync);
+    coop_fft_inverse<Q2, C, C, true>(v, xr, nullptr, tws, q, c, bsync, twt);
 #pragma unroll
     for (int a = 0; a < 32; ++a) st_stream(base + (int64_t)(Q2 * a + q) * N1, v[a]);
 }
