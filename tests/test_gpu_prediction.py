@@ -1,0 +1,53 @@
+"""The predicted-last-iteration launch protocol of the fused step loop (TM_ITERF chaining the next step,
+TM_ROT recovery after a wrong prediction) must not change anything observable: same step / iteration counts
+and bit-identical fields as the plain protocol (OCB_PREDICT=0), forwards and backwards.  The backward (DBP)
+case has a growing power profile inside each span, so the iteration count rises along the span and the
+wrong-prediction path is exercised."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(direction, predict, n, hz, ltot, pdbm):
+    import torch
+
+    from opticommpy_b200.channels import manakov_rows_device
+    from opticommpy_b200.utils import parameters
+
+    rng = np.random.default_rng(5)
+    p_lin = 1e-3 * 10 ** (pdbm / 10)
+    x = (rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n))) * np.sqrt(p_lin / 4)
+    rows = torch.from_numpy(x.astype(np.complex64)).cuda()
+    p = parameters()
+    p.Fs, p.Ltotal, p.Lspan, p.hz = 64e9, ltot, ltot / 2, hz
+    p.alpha, p.D, p.gamma, p.Fc = 0.2, 16, 1.3, 193.1e12
+    p.amp, p.NF, p.maxIter, p.tol, p.nlprMethod, p.maxNlinPhaseRot = "ideal", 4.5, 10, 1e-5, False, 2e-2
+    os.environ["OCB_PREDICT"] = "1" if predict else "0"
+    try:
+        st = manakov_rows_device(rows, p, direction)
+    finally:
+        os.environ.pop("OCB_PREDICT", None)
+    torch.cuda.synchronize()
+    return torch.view_as_real(rows).cpu().numpy(), st
+
+
+@pytest.mark.parametrize("direction", [+1, -1])
+@pytest.mark.parametrize("n", [1 << 16, 1 << 18])
+def test_prediction_is_invisible(direction, n):
+    ref, st0 = _run(direction, False, n, 1.0, 100.0, 12.0)
+    out, st1 = _run(direction, True, n, 1.0, 100.0, 12.0)
+    assert st0["steps"] == st1["steps"] == 100
+    assert st0["iterations"] == st1["iterations"]
+    assert st0["nonconverged"] == st1["nonconverged"]
+    assert st0["iterations"] > 2 * st0["steps"]  # the nonlinearity is active: several iterations per step
+    assert np.array_equal(out, ref)
+
+
+def test_iteration_count_varies_within_span():
+    """Sanity of the test itself: backwards, the per-step iteration count is not constant (so some predictions fail)."""
+    _, a = _run(-1, True, 1 << 16, 1.0, 100.0, 12.0)
+    _, b = _run(-1, True, 1 << 16, 1.0, 20.0, 12.0)
+    assert a["iterations"] / a["steps"] != b["iterations"] / b["steps"]
