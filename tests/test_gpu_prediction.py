@@ -35,19 +35,17 @@ def _run(direction, predict, n, hz, ltot, pdbm):
 
 
 @pytest.mark.parametrize("direction", [+1, -1])
-@pytest.mark.parametrize("n", [1 << 16, 1 << 18])
-def test_prediction_is_invisible(direction, n):
-    ref, st0 = _run(direction, False, n, 1.0, 100.0, 12.0)
-    out, st1 = _run(direction, True, n, 1.0, 100.0, 12.0)
+@pytest.mark.parametrize("n,pdbm", [(1 << 16, 12.0), (1 << 16, -3.0), (1 << 18, -3.0)])
+def test_prediction_is_invisible(direction, n, pdbm):
+    ref, st0 = _run(direction, False, n, 1.0, 100.0, pdbm)
+    out, st1 = _run(direction, True, n, 1.0, 100.0, pdbm)
     assert st0["steps"] == st1["steps"] == 100
     assert st0["iterations"] == st1["iterations"]
     assert st0["nonconverged"] == st1["nonconverged"]
-    assert st0["iterations"] > 2 * st0["steps"]  # the nonlinearity is active: several iterations per step
+    if pdbm < 0:
+        # the iteration count changes inside each span (3 -> 2 forwards: early convergence; 2 -> 3 backwards:
+        # wrong prediction and TM_ROT recovery), so both off-nominal paths of the protocol are exercised
+        assert 2 * st0["steps"] < st0["iterations"] < 3 * st0["steps"]
+    else:
+        assert st0["iterations"] == 3 * st0["steps"]
     assert np.array_equal(out, ref)
-
-
-def test_iteration_count_varies_within_span():
-    """Sanity of the test itself: backwards, the per-step iteration count is not constant (so some predictions fail)."""
-    _, a = _run(-1, True, 1 << 16, 1.0, 100.0, 12.0)
-    _, b = _run(-1, True, 1 << 16, 1.0, 20.0, 12.0)
-    assert a["iterations"] / a["steps"] != b["iterations"] / b["steps"]
