@@ -26,11 +26,16 @@ int launch_time(int Q1, const TimeArgs& a, cudaStream_t st) {
     }
     return fail("fused engine: unsupported N1", __FILE__, __LINE__);
 }
-template <int Q2>
+// W positions per k_freq tile of the main kernels when N2 = 1024: 16 (128-byte row segments, one 512-thread CTA
+// per SM; default) or 8 (64-byte segments, two 256-thread CTAs per SM); OCB_FREQ_C is a tuning knob read once
+int freq_c() {
+    static const int c = (getenv("OCB_FREQ_C") && atoi(getenv("OCB_FREQ_C")) == 8) ? 8 : 16;  // 16 measured 7 % faster per pass
+    return c;
+}
+template <int Q2, int C>
 int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP, const long long* flag,
                   long long step_id, const long long* need_flag, long long need_id, cudaStream_t st) {
     static bool configured = false;
-    constexpr int C = kFreqC;
     const size_t smem = FreqCfg<Q2, C>::SMEM_BYTES;
     if (!configured) {
         OCB_CUDA(cudaFuncSetAttribute(k_freq<Q2, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -42,10 +47,11 @@ int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP,
 int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st,
                 const long long* flag = nullptr, long long step_id = 0, const long long* need_flag = nullptr,
                 long long need_id = 0) {
+    if (freq_c() == 16 && Q2 == 32) return launch_freq_t<32, 16>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
     switch (Q2) {
-        case 8: return launch_freq_t<8>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
-        case 16: return launch_freq_t<16>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
-        case 32: return launch_freq_t<32>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
+        case 8: return launch_freq_t<8, kFreqC>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
+        case 16: return launch_freq_t<16, kFreqC>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
+        case 32: return launch_freq_t<32, kFreqC>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
     }
     return fail("fused engine: unsupported N2", __FILE__, __LINE__);
 }
@@ -55,7 +61,8 @@ int launch_linop_perm(ocb_ssfm_plan* p, float2* LP, double a, double b, double F
         OCB_LAUNCH(k_tab_linop_perm_s, grid_for(p->N, 256, 1), 256, 0, st, LP, kFreqC, p->N, a, b, Fs, h, scale);
         return 0;
     }
-    OCB_LAUNCH(k_tab_linop_perm, grid_for(p->N, 256, 1), 256, 0, st, LP, p->q1, p->q2, kFreqC, p->N, a, b, Fs, h, scale);
+    OCB_LAUNCH(k_tab_linop_perm, grid_for(p->N, 256, 1), 256, 0, st, LP, p->q1, p->q2,
+               (p->q2 == 32 ? freq_c() : kFreqC), p->N, a, b, Fs, h, scale);
     return 0;
 }
 // natural planar rows [r][N2*n1 + n2] -> engine layout [r][N1*n2 + n1] (to_engine) or back

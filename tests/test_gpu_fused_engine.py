@@ -122,3 +122,32 @@ def test_profiled_and_split_variants_agree(api):
         api.eng.clear_plans()
     assert rel_l2(out_s, ref) < 2e-6
     api.eng.set_default_engine("auto")
+
+
+def test_full_size_fused_vs_cufft_engine(api):
+    """N = 2^20 (the 512-thread frequency pass with 128-byte row segments) against the cuFFT-driven engine."""
+    x = field(9, 1 << 20, 2, 6e-3)
+    r = both(api, api.manakovSSF, x, Fs=512e9, Ltotal=1.6, Lspan=0.8, hz=0.08, amp="ideal", nlprMethod=False,
+             saveSpanN=[], prgsBar=False)
+    assert rel_l2(r["fused"][0], r["cufft"][0]) < 2e-5
+    assert r["fused"][1]._b200_stats["steps"] == r["cufft"][1]._b200_stats["steps"] == 22
+    assert r["fused"][1]._b200_stats["iterations"] == r["cufft"][1]._b200_stats["iterations"]
+
+
+def test_kernel_variants_are_bit_identical(api):
+    """Tuning options that must not change a single bit: the persistent cp.async-pipelined time kernels
+    (OCB_TPIPE=1) and programmatic dependent launch switched off (OCB_PDL=0)."""
+    import os
+    x = field(11, 1 << 20, 2, 6e-3)
+    kw = dict(Fs=512e9, Ltotal=1.6, Lspan=0.8, hz=0.08, amp="ideal", nlprMethod=False, saveSpanN=[], prgsBar=False)
+    api.eng.set_default_engine("fused")
+    ref = api.manakovSSF(x, Bag(**kw))
+    for var in ({"OCB_TPIPE": "1"}, {"OCB_TPIPE": "1", "OCB_TPIPE_SH": "0"}, {"OCB_PDL": "0"}):
+        os.environ.update(var)
+        try:
+            out = api.manakovSSF(x, Bag(**kw))
+        finally:
+            for k in var:
+                del os.environ[k]
+        assert np.array_equal(out, ref), var
+    api.eng.set_default_engine("auto")
