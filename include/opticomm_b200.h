@@ -254,6 +254,15 @@ int ocb_ber_count(const void* rx_dev, const void* tx_dev, int dtype, int64_t L, 
                   int M, int rotate, double sqrtEs, double* ber_host, double* ser_host, double* snr_host,
                   int64_t* counts_host, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- Rx front-end glue --------------------------------------
+ * decimate: maximum-variance sampling instant per mode + downsampling.
+ * Replaces: optic.dsp.core.decimate (optic/dsp/core.py:435-491).
+ * x_rows: planar [nModes][N] complex64; y_rows: [nModes][ceil(N/decFactor)]; delays_dev: int32[nModes].
+ * (firFilter, optic/dsp/core.py:87-125, is fftconvolve(x, h, 'same') per mode = ocb_edc_run with taps h.) */
+int64_t ocb_decimate_workspace_bytes(int nModes, int SpSin);
+int ocb_decimate_run(const void* x_rows, void* y_rows, int64_t N, int nModes, int SpSin, int decFactor,
+                     void* delays_dev, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

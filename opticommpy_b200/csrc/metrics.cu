@@ -261,3 +261,83 @@ extern "C" int ocb_ber_count(const void* rx_dev, const void* tx_dev, int dtype, 
     }
     return 0;
 }
+
+// =============================================================================================
+// Rx front-end glue: decimate (optic/dsp/core.py:435-491).
+//   varVector[p] = var(sigIn[p::SpSin, k])  (numpy var of a complex column: mean |x - mean|^2)
+//   sampDelay[k] = first p with varVector[p] == max      (maximum-variance sampling instant)
+//   sigOut[i, k] = roll(sigIn[:, k], -sampDelay[k])[i * decFactor]
+// Planar rows x[nModes][N] complex64 in, y[nModes][ceil(N / decFactor)] out; sums in float64.
+// =============================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_phase_moments(const float2* __restrict__ x, int64_t N, int SpSin, double* __restrict__ mom /* [nModes][SpSin][3] */) {
+    const int p = blockIdx.x, mode = blockIdx.y;
+    const float2* xs = x + (int64_t)mode * N;
+    double sr = 0.0, si = 0.0, sq = 0.0;
+    for (int64_t i = p + (int64_t)threadIdx.x * SpSin; i < N; i += (int64_t)blockDim.x * SpSin) {
+        const float2 v = xs[i];
+        sr += (double)v.x; si += (double)v.y;
+        sq += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+    }
+    __shared__ double sh[3][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    sr = warp_sum(sr); si = warp_sum(si); sq = warp_sum(sq);
+    if (lane == 0) { sh[0][wid] = sr; sh[1][wid] = si; sh[2][wid] = sq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; c += sh[2][w]; }
+        double* o = mom + ((int64_t)mode * SpSin + p) * 3;
+        o[0] = a; o[1] = b; o[2] = c;
+    }
+}
+__global__ void k_pick_delay(const double* __restrict__ mom, int64_t N, int SpSin, int nModes, int32_t* __restrict__ delay) {
+    const int mode = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode >= nModes) return;
+    const double cnt = (double)(N / SpSin);
+    double best = -1.0;
+    int bi = 0;
+    for (int p = 0; p < SpSin; ++p) {
+        const double* o = mom + ((int64_t)mode * SpSin + p) * 3;
+        const double mr = o[0] / cnt, mi = o[1] / cnt;
+        const double var = o[2] / cnt - (mr * mr + mi * mi);
+        if (var > best) { best = var; bi = p; }  // first index of the maximum (core.py:477)
+    }
+    delay[mode] = bi;
+}
+__global__ void k_decimate_gather(const float2* __restrict__ x, float2* __restrict__ y, int64_t N, int64_t Nout,
+                                  int decFactor, int nModes, const int32_t* __restrict__ delay) {
+    const int64_t total = Nout * nModes;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t mode = i / Nout, j = i % Nout;
+        int64_t src = j * decFactor + delay[mode];  // np.roll(x, -d)[j*dec] = x[(j*dec + d) mod N]
+        if (src >= N) src -= N;
+        y[mode * Nout + j] = x[mode * N + src];
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t ocb_decimate_workspace_bytes(int nModes, int SpSin) {
+    if (nModes <= 0 || SpSin <= 0) return -1;
+    return (int64_t)nModes * SpSin * 3 * (int64_t)sizeof(double) + 256;
+}
+
+extern "C" int ocb_decimate_run(const void* x_rows, void* y_rows, int64_t N, int nModes, int SpSin, int decFactor,
+                                void* delays_dev, void* workspace, int64_t workspace_bytes, void* stream) {
+    OCB_REQUIRE(x_rows && y_rows && delays_dev && workspace, "decimate_run: NULL argument");
+    OCB_REQUIRE(N > 0 && nModes > 0 && SpSin > 0 && decFactor > 0, "decimate_run: bad sizes");
+    OCB_REQUIRE(N % SpSin == 0, "decimate_run: the signal length must be a multiple of SpSin (reshape(-1, SpSin), core.py:475)");
+    OCB_REQUIRE(SpSin <= 65535 && nModes <= 65535, "decimate_run: SpSin / nModes too large");
+    OCB_REQUIRE(workspace_bytes >= ocb_decimate_workspace_bytes(nModes, SpSin), "decimate_run: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* mom = (double*)workspace;
+    const int64_t Nout = (N + decFactor - 1) / decFactor;
+    OCB_LAUNCH(k_phase_moments, dim3(SpSin, nModes), 256, 0, st, (const float2*)x_rows, N, SpSin, mom);
+    OCB_LAUNCH(k_pick_delay, (nModes + 63) / 64, 64, 0, st, mom, N, SpSin, nModes, (int32_t*)delays_dev);
+    OCB_LAUNCH(k_decimate_gather, grid_for(Nout * nModes, 256, 2), 256, 0, st, (const float2*)x_rows, (float2*)y_rows, N,
+               Nout, decFactor, nModes, (const int32_t*)delays_dev);
+    return 0;
+}

@@ -1,0 +1,69 @@
+"""Generate tests/golden/ref_frontend.npz (Rx front-end glue) by running the UNMODIFIED
+reference (/root/reference) on seeded inputs.  Build container only:
+
+    NUMBA_CACHE_DIR=/tmp/nbcache PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_frontend.py
+
+Same import recipe as make_golden.py (plotting modules stubbed, numba cache in scratch).
+"""
+import os
+import sys
+from unittest.mock import MagicMock
+
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/nbcache")
+sys.dont_write_bytecode = True
+for _m in ["matplotlib", "matplotlib.pyplot", "matplotlib.mlab", "matplotlib.cm", "matplotlib.colors",
+           "matplotlib.animation", "mpl_scatter_density", "simple_pid", "prettytable"]:
+    sys.modules[_m] = MagicMock()
+sys.path.insert(0, os.environ.get("OPTICOMMPY_REF", "/root/reference"))
+
+import numpy as np  # noqa: E402
+
+from optic.dsp.core import decimate, firFilter, pulseShape  # noqa: E402
+from optic.utils import parameters  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_frontend.npz")
+G = {}
+rng = np.random.default_rng(77)
+
+
+def rrc(sps, ntaps, rolloff):
+    q = parameters()
+    q.pulseType, q.SpS, q.nFilterTaps, q.rollOff = "rrc", sps, ntaps, rolloff
+    return pulseShape(q)
+
+
+# firFilter: root-raised-cosine matched filter (even and odd tap counts), complex and real taps, 1-D and 2-D inputs
+x = (rng.normal(size=(6000, 2)) + 1j * rng.normal(size=(6000, 2))).astype(np.complex128)
+G["fir_in"] = x
+h_rrc = rrc(8, 257, 0.1)
+h_rrc = h_rrc / np.max(np.abs(h_rrc))
+G["fir_h_rrc"] = h_rrc
+G["fir_rrc"] = firFilter(h_rrc, x)
+h_even = rng.normal(size=64) + 1j * rng.normal(size=64)
+G["fir_h_even"] = h_even
+G["fir_even_1d"] = firFilter(h_even, x[:, 0])
+G["fir_real_in"] = firFilter(h_rrc, x.real.copy())
+G["fir_c64"] = firFilter(h_rrc.astype(np.float32), x.astype(np.complex64))
+
+# decimate: 16 -> 2 samples per symbol on a pulse-shaped 2-mode signal with different timing offsets per mode
+sps = 16
+nsym = 2048
+sym = (rng.integers(0, 2, size=(nsym, 2)) * 2 - 1) + 1j * (rng.integers(0, 2, size=(nsym, 2)) * 2 - 1)
+up = np.zeros((nsym * sps, 2), dtype=complex)
+up[::sps] = sym
+pulse = rrc(sps, 1025, 0.2)
+sig = firFilter(pulse / np.max(np.abs(pulse)), up)
+sig = firFilter(pulse / np.sum(pulse), sig)
+sig[:, 1] = np.roll(sig[:, 1], 5)
+sig += 0.02 * (rng.normal(size=sig.shape) + 1j * rng.normal(size=sig.shape))
+G["dec_in"] = sig
+p = parameters()
+p.SpSin, p.SpSout = sps, 2
+G["dec_16_2"] = decimate(sig, p)
+p.SpSout = 1
+G["dec_16_1_1d"] = decimate(sig[:, 1], p)
+p.SpSin, p.SpSout = 4, 2
+G["dec_4_2"] = decimate(sig[: 4 * 1000], p)
+
+np.savez_compressed(OUT, **G)
+print({k: (v.shape, v.dtype) for k, v in G.items()})
