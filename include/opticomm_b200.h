@@ -215,6 +215,19 @@ int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hwl, void* y,
                     float mu, const void* constSymb, int M, const void* radii, int nR, float Rcma,
                     int runWL, void* stream);
 
+/* ocb_mimo_eq_rls_run: one RLS ('rls', decision_directed = 0, error against ref) or DD-RLS ('dd-rls',
+ * decision_directed = 1) training stage.  Replaces coreAdaptEq with rlsUp / ddrlsUp
+ * (optic/dsp/equalization.py:354-516, 576-644, 712-785).  Same buffer conventions as ocb_mimo_eq_run; the
+ * inverse correlation matrices start from the identity in every call (like the reference's 'rls' branch,
+ * :447-451) and live on the device only.  nTaps <= 32.  workspace: the gain vectors Y_N(s),
+ * ocb_mimo_eq_rls_workspace_bytes(nStreams, nModes, L) bytes.                                              */
+int64_t ocb_mimo_eq_rls_workspace_bytes(int nStreams, int nModes, int64_t L);
+int ocb_mimo_eq_rls_run(const void* x, const void* ref, void* H, void* y, void* errSq, void* Hiter,
+                        int nStreams, int64_t nSamp, int64_t x_stream_stride, int64_t ref_stream_stride,
+                        int64_t y_stream_stride, int64_t err_stream_stride, int64_t err_mode_stride,
+                        int64_t L, int nModes, int nTaps, int SpS, int decision_directed, float lambda,
+                        const void* constSymb, int M, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- blind phase search ----------------------------------------------------------------------
  * Replaces optic.dsp.carrierRecovery.bps (carrierRecovery.py:172-223).
  *   x     : (L, nModes) complex128 (double pairs) device array, modes interleaved as in the reference

@@ -457,8 +457,42 @@ int launch_mimo(bool wl, cudaStream_t st, const float2* X, const float2* REF, fl
 }
 
 #include "rxdsp_eq_la.cuh"
+#include "rxdsp_rls.cuh"
 
 }  // namespace
+
+extern "C" int64_t ocb_mimo_eq_rls_workspace_bytes(int nStreams, int nModes, int64_t L) {
+    if (nStreams <= 0 || nModes <= 0 || L < 0) return -1;
+    return (int64_t)nStreams * nModes * L * 32 * (int64_t)sizeof(float2) + 256;
+}
+
+extern "C" int ocb_mimo_eq_rls_run(const void* x, const void* ref, void* H, void* y, void* errSq, void* Hiter,
+                                   int nStreams, int64_t nSamp, int64_t x_stream_stride, int64_t ref_stream_stride,
+                                   int64_t y_stream_stride, int64_t err_stream_stride, int64_t err_mode_stride,
+                                   int64_t L, int nModes, int nTaps, int SpS, int decision_directed, float lambda,
+                                   const void* constSymb, int M, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+    OCB_REQUIRE(x && H && y && errSq && workspace, "mimo_eq_rls_run: NULL argument");
+    OCB_REQUIRE(nStreams > 0 && L >= 0 && nSamp > 0, "mimo_eq_rls_run: bad sizes");
+    OCB_REQUIRE(nModes == 1 || nModes == 2 || nModes == 4, "mimo_eq_rls_run: nModes must be 1, 2 or 4");
+    OCB_REQUIRE(nTaps >= 1 && nTaps <= 32, "mimo_eq_rls_run: nTaps must be in [1, 32] (one matrix row per lane)");
+    OCB_REQUIRE(SpS >= 1 && lambda > 0.f, "mimo_eq_rls_run: SpS must be >= 1 and lambda > 0");
+    OCB_REQUIRE(L == 0 || (L - 1) * SpS + nTaps <= nSamp, "mimo_eq_rls_run: window runs past the end of the input");
+    if (decision_directed) OCB_REQUIRE(constSymb && M >= 1, "mimo_eq_rls_run: constellation required for dd-rls");
+    else OCB_REQUIRE(ref != nullptr, "mimo_eq_rls_run: reference symbols required for rls");
+    OCB_REQUIRE(workspace_bytes >= ocb_mimo_eq_rls_workspace_bytes(nStreams, nModes, L), "mimo_eq_rls_run: workspace too small");
+    if (L == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define OCB_RLS_CASE(NM_)                                                                                          \
+    if (nModes == NM_)                                                                                             \
+        return launch_rls<NM_>(st, (const float2*)x, (const float2*)ref, (float2*)workspace, (float2*)H, (float2*)y, \
+                               (float*)errSq, (float2*)Hiter, nStreams, x_stream_stride, ref_stream_stride,        \
+                               y_stream_stride, err_stream_stride, err_mode_stride, L, nTaps, SpS,                 \
+                               decision_directed != 0, lambda, (const float2*)constSymb, M);
+    OCB_RLS_CASE(1) OCB_RLS_CASE(2) OCB_RLS_CASE(4)
+#undef OCB_RLS_CASE
+    return fail("mimo_eq_rls_run: unsupported nModes", __FILE__, __LINE__);
+}
 
 extern "C" int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hwl, void* y, void* errSq,
                                void* Hiter, int nStreams, int64_t nSamp, int64_t x_stream_stride,

@@ -153,7 +153,7 @@ def _parse_equalizer_args(sigIn, param, symbRef):
 
     # The casts to prec=complex64 (:222-223) and the zero padding of floor(nTaps/2) rows (:227-231) are
     # done on the device: the raw arrays are uploaded as they are (numpy's complex astype is slow).
-    needs_ref = any(a in ("nlms", "da-rde") for a in (s.alg if isinstance(s.alg, list) else []))
+    needs_ref = any(a in ("nlms", "da-rde", "rls") for a in (s.alg if isinstance(s.alg, list) else []))
     s.symbRef = _engine.as_host_complex(symbRef) if needs_ref else None
     s.sig = _engine.as_host_complex(sigIn)
     s.mu = np.atleast_1d(np.array(mu).astype(np.float32))
@@ -191,7 +191,11 @@ def _parse_equalizer_args(sigIn, param, symbRef):
         raise TypeError("param.alg must be a list of algorithm names, e.g. ['cma', 'rde']")
     for a in s.alg:
         if a in ("rls", "dd-rls"):
-            raise NotImplementedError(f"'{a}' is not part of the B200 hot path yet (SURVEY.md §8f rank 4)")
+            if s.nTaps > 32:
+                raise NotImplementedError("'rls'/'dd-rls' on the GPU keep one matrix row per lane: nTaps <= 32")
+            if s.runWL:
+                raise NotImplementedError("'rls'/'dd-rls' have no widely-linear update in the reference (rlsUp ignores H_)")
+            continue
         if a not in _cabi.ALG_IDS:
             raise ValueError("Equalization algorithm not specified (or incorrectly specified).")
     if len(s.L) < len(s.alg) or len(s.mu) < len(s.alg):
@@ -246,7 +250,7 @@ def _run_equalizer_batch(setups):
         nEnd = nStart + Ls
         if nEnd > total or (Ls > 0 and (nEnd - 1) * SpS + nT > nSamp):
             raise IndexError("training section runs past the end of the signal")
-        if name in ("nlms", "da-rde") and nEnd > Lref:
+        if name in ("nlms", "da-rde", "rls") and nEnd > Lref:
             raise IndexError("reference symbol sequence shorter than the training section")
         reps = s0.numIter if stage == 0 else 1
         for rep in range(reps):
@@ -254,6 +258,24 @@ def _run_equalizer_batch(setups):
             d_hit = None
             if s0.storeCoeff:
                 d_hit = torch.empty((nS, Ls, nM * nM, nT, 2), dtype=torch.float32, device="cuda")
+            if name in ("rls", "dd-rls"):
+                ws_bytes = int(lib.ocb_mimo_eq_rls_workspace_bytes(nS, nM, Ls))
+                d_ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+                ws_ptr = (d_ws.data_ptr() + 255) // 256 * 256
+                lam = float(np.float32(s0.lambdaRLS))  # the reference casts lambda to prec (:225)
+                _cabi.check(
+                    lib.ocb_mimo_eq_rls_run(
+                        _ptr(d_x, nStart * SpS * nM * 8), _ptr(d_ref, nStart * nM * 8) if d_ref is not None else None,
+                        _ptr(d_H), _ptr(d_y, nStart * nM * 8), _ptr(d_e, nStart * 4),
+                        _ptr(d_hit) if d_hit is not None else None,
+                        nS, nSamp - nStart * SpS, nSamp * nM, Lref * nM, total * nM, nM * total, total,
+                        Ls, nM, nT, SpS, int(name == "dd-rls"), lam, _ptr(d_c), len(s0.constSymb),
+                        _vp(ws_ptr), ws_bytes, st,
+                    ),
+                    "ocb_mimo_eq_rls_run",
+                )
+                hiter = d_hit
+                continue
             _cabi.check(
                 lib.ocb_mimo_eq_run(
                     _ptr(d_x, nStart * SpS * nM * 8), _ptr(d_ref, nStart * nM * 8) if d_ref is not None else None, _ptr(d_H),
@@ -303,8 +325,9 @@ def mimoAdaptEqualizer(sigIn, param=None, symbRef=None):
     alg [['nlms']], constType ['qam'], M [4], shapingFactor [0], prgsBar [True],
     returnResults [False], prec [np.complex64].
 
-    Algorithms: 'cma', 'rde', 'nlms', 'dd-lms', 'da-rde', 'static' (list form only; one entry of
-    ``L`` and ``mu`` per stage).  Returns ``sigOut`` or, with ``returnResults``,
+    Algorithms: 'cma', 'rde', 'nlms', 'dd-lms', 'da-rde', 'rls', 'dd-rls', 'static' (list form only; one
+    entry of ``L`` and ``mu`` per stage; 'rls'/'dd-rls': nTaps <= 32, forgetting factor ``lambdaRLS``, the inverse
+    correlation matrices start from the identity in every stage).  Returns ``sigOut`` or, with ``returnResults``,
     ``(sigOut, H, errSq, Hiter)`` / ``(sigOut, H, H_, errSq, Hiter)`` in widely-linear mode.
     """
     logg.info("Running adaptive equalizer...")

@@ -122,8 +122,43 @@ def core_adapt_eq(x, ref, H, Hwl, L, SpS, alg, mu, constSymb, runWL=False, store
     return y, H, Hwl, err, (Hiter if storeCoeff else H[..., None].copy())
 
 
+def rls_stage(x, ref, H, L, SpS, lam, constSymb, dd=False, storeCoeff=False):
+    """One 'rls' (dd=False) or 'dd-rls' (dd=True) stage, float64 restatement of coreAdaptEq + rlsUp / ddrlsUp
+    (optic/dsp/equalization.py:461-473, 576-644, 712-785).  Sd starts from the identity per input mode
+    (:447-451; the reference leaves it undefined for 'dd-rls' — the identity is used for both here)."""
+    nT = H.shape[1]
+    nM = x.shape[1]
+    H = H.astype(np.complex128).copy()
+    Sd = [np.eye(nT, dtype=np.complex128) for _ in range(nM)]
+    y = np.zeros((L, nM), dtype=np.complex128)
+    err2 = np.zeros((nM, L))
+    Hiter = np.zeros((nM * nM, nT, L), dtype=np.complex128) if storeCoeff else None
+    for ind in range(L):
+        win = x[ind * SpS: ind * SpS + nT, :]
+        out = np.array([sum(H[m + N * nM] @ win[:, N] for N in range(nM)) for m in range(nM)])  # :464-468
+        y[ind] = out
+        if dd:
+            target = np.array([constSymb[np.argmin(np.abs(out[m] - constSymb))] for m in range(nM)])  # :751-753
+        else:
+            target = ref[ind]
+        err = target - out  # :614 / :754
+        for N in range(nM):
+            u = np.conj(win[:, N])                       # :627
+            A = Sd[N] @ u                                # :632
+            B = np.conj(u) @ Sd[N]                       # :633
+            C = np.conj(u) @ A                           # :634
+            Sd[N] = (Sd[N] - np.outer(A, B) / (lam + C)) / lam   # :635-637
+            Yv = Sd[N] @ u                               # :639
+            for m in range(nM):
+                H[m + N * nM] += err[m] * Yv             # :641
+        err2[:, ind] = np.abs(err) ** 2
+        if storeCoeff:
+            Hiter[:, :, ind] = H
+    return y, H, err2, Hiter
+
+
 def mimo_adapt_equalizer(sigIn, symbRef, constSymb, nTaps=15, SpS=2, alg=("nlms",), mu=(1e-3,), L=None,
-                         numIter=1, runWL=False, storeCoeff=False, H=None, shapingFactor=0.0):
+                         numIter=1, runWL=False, storeCoeff=False, H=None, shapingFactor=0.0, lambdaRLS=0.99):
     """Stage driver restated from optic/dsp/equalization.py:205-319: orientation, casts
     (float32 step sizes), zero padding of floor(nTaps/2) rows, centre-spike taps, stages with the
     taps carried over and stage 0 repeated ``numIter`` times.  ``constSymb`` is the raw
@@ -165,6 +200,12 @@ def mimo_adapt_equalizer(sigIn, symbRef, constSymb, nTaps=15, SpS=2, alg=("nlms"
     for stage, name in enumerate(alg):
         n1 = n0 + int(L[stage])
         for _ in range(numIter if stage == 0 else 1):
+            if name in ("rls", "dd-rls"):
+                ys, H, es, Hiter = rls_stage(x[n0 * SpS:(n1 + 2 * Lpad) * SpS], ref[n0:n1], H, n1 - n0, SpS,
+                                             float(np.float32(lambdaRLS)), c, name == "dd-rls", storeCoeff)
+                y[n0:n1] = ys
+                err[:, n0:n1] = es
+                continue
             ys, H, Hwl, es, Hiter = core_adapt_eq(x[n0 * SpS:(n1 + 2 * Lpad) * SpS], ref[n0:n1], H, Hwl, n1 - n0, SpS,
                                                    name, mu[stage], c, runWL, storeCoeff)
             y[n0:n1] = ys

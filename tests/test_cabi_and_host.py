@@ -84,5 +84,9 @@ def test_equalizer_argument_parsing(golden):
     assert s.H[0, 7] == 1 and s.H[3, 7] == 1 and np.count_nonzero(s.H) == 2
     assert s.mu.dtype == np.float32 and len(s.Rrde) == 3
     assert s.Rcma == pytest.approx(1.32, abs=1e-6)
-    with pytest.raises(NotImplementedError):
-        _parse_equalizer_args(golden["eq_in"], Bag(alg=["rls"], mu=[1e-3]), None)
+    s = _parse_equalizer_args(golden["eq_in"], Bag(alg=["rls"], mu=[1e-3]), golden["eq_ref"])
+    assert s.symbRef is not None and s.lambdaRLS == 0.99      # 'rls' trains against the reference symbols
+    with pytest.raises(NotImplementedError):                  # one matrix row per lane: nTaps <= 32
+        _parse_equalizer_args(golden["eq_in"], Bag(alg=["rls"], mu=[1e-3], nTaps=33), None)
+    with pytest.raises(NotImplementedError):                  # rlsUp has no widely-linear update
+        _parse_equalizer_args(golden["eq_in"], Bag(alg=["dd-rls"], mu=[1e-3], runWL=True), None)
