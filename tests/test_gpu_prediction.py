@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(direction, predict, n, hz, ltot, pdbm):
+def _run(direction, predict, n, hz, ltot, pdbm, maxIter=10):
     import torch
 
     from opticommpy_b200.channels import manakov_rows_device
@@ -24,7 +24,7 @@ def _run(direction, predict, n, hz, ltot, pdbm):
     p = parameters()
     p.Fs, p.Ltotal, p.Lspan, p.hz = 64e9, ltot, ltot / 2, hz
     p.alpha, p.D, p.gamma, p.Fc = 0.2, 16, 1.3, 193.1e12
-    p.amp, p.NF, p.maxIter, p.tol, p.nlprMethod, p.maxNlinPhaseRot = "ideal", 4.5, 10, 1e-5, False, 2e-2
+    p.amp, p.NF, p.maxIter, p.tol, p.nlprMethod, p.maxNlinPhaseRot = "ideal", 4.5, maxIter, 1e-5, False, 2e-2
     os.environ["OCB_PREDICT"] = "1" if predict else "0"
     try:
         st = manakov_rows_device(rows, p, direction)
@@ -48,4 +48,16 @@ def test_prediction_is_invisible(direction, n, pdbm):
         assert 2 * st0["steps"] < st0["iterations"] < 3 * st0["steps"]
     else:
         assert st0["iterations"] == 3 * st0["steps"]
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("maxIter", [1, 2, 3])
+def test_prediction_with_iteration_limit(maxIter):
+    """Steps that hit maxIter without converging (channels.py:431-434): the predicted-last iteration is then the
+    last allowed one and does not converge; counts and fields must still equal the plain protocol's."""
+    ref, st0 = _run(+1, False, 1 << 16, 1.0, 100.0, 12.0, maxIter)
+    out, st1 = _run(+1, True, 1 << 16, 1.0, 100.0, 12.0, maxIter)
+    assert st0 == st1
+    if maxIter < 3:
+        assert st0["nonconverged"] == st0["steps"] == 100 and st0["iterations"] == maxIter * 100
     assert np.array_equal(out, ref)
