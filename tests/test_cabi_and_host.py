@@ -90,3 +90,15 @@ def test_equalizer_argument_parsing(golden):
         _parse_equalizer_args(golden["eq_in"], Bag(alg=["rls"], mu=[1e-3], nTaps=33), None)
     with pytest.raises(NotImplementedError):                  # rlsUp has no widely-linear update
         _parse_equalizer_args(golden["eq_in"], Bag(alg=["dd-rls"], mu=[1e-3], runWL=True), None)
+
+
+def test_frontend_argument_errors():
+    """Errors of the Rx front-end mirrors that the reference raises before any arithmetic (no GPU needed)."""
+    from opticommpy_b200.core import decimate, firFilter
+    x = np.ones((4001, 2), dtype=complex)
+    with pytest.raises(ValueError):   # numpy's reshape(-1, SpSin) error in the reference (core.py:475)
+        decimate(x, Bag(SpSin=4, SpSout=2))
+    with pytest.raises(ValueError):
+        firFilter(np.ones(5000), x)   # filter longer than the signal: not supported on the GPU path
+    with pytest.raises(ValueError):
+        firFilter(np.ones(0), x)
