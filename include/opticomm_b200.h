@@ -267,6 +267,10 @@ int ocb_ber_count(const void* rx_dev, const void* tx_dev, int dtype, int64_t L, 
                   int M, int rotate, double sqrtEs, double* ber_host, double* ser_host, double* snr_host,
                   int64_t* counts_host, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ocb_pnorm_run replaces optic.dsp.core.pnorm (optic/dsp/core.py:702-717): x / sqrt(mean |x|^2) over the whole
+ * array, in place.  x_dev: n complex128 ; workspace: at least 4096 doubles.                                      */
+int ocb_pnorm_run(void* x_dev, int64_t n, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Rx front-end glue --------------------------------------
  * decimate: maximum-variance sampling instant per mode + downsampling.
  * Replaces: optic.dsp.core.decimate (optic/dsp/core.py:435-491).

@@ -69,6 +69,7 @@ SIGNATURES = {
     "ocb_mimo_eq_rls_workspace_bytes": (_i64, [_i, _i, _i64]),
     "ocb_mimo_eq_rls_run": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i, _i, _i, _i,
                                 C.c_float, _vp, _i, _vp, _i64, _vp]),
+    "ocb_pnorm_run": (_i, [_vp, _i64, _vp, _i64, _vp]),
     "ocb_decimate_workspace_bytes": (_i64, [_i, _i]),
     "ocb_decimate_run": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "ocb_ssfm_plan_pass_time": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _vp]),

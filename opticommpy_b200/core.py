@@ -1,5 +1,5 @@
-"""Drop-in mirrors of the Rx front-end glue in ``optic.dsp.core``: ``firFilter`` (optic/dsp/core.py:87-125) and
-``decimate`` (:435-491) — SURVEY.md §8f rank 3, the calls between the fiber model and ``edc`` in the reference
+"""Drop-in mirrors of the Rx front-end glue in ``optic.dsp.core``: ``firFilter`` (optic/dsp/core.py:87-125),
+``decimate`` (:435-491) and ``pnorm`` (:702-717) — SURVEY.md §8f rank 3, the calls between the fiber model and ``edc`` in the reference
 notebooks.  numpy in, numpy out; the arithmetic runs on the GPU through the C-ABI (``ocb_edc_run`` — an
 overlap-save linear convolution — and ``ocb_decimate_run``).
 """
@@ -108,3 +108,23 @@ def decimate(sigIn, param):
     else:
         sigOut = out.real.astype(sigIn.dtype)
     return sigOut.flatten() if input1D else sigOut
+
+
+def pnorm(x):
+    """
+    Normalise the average power: ``x / sqrt(mean(|x|^2))`` with the mean over the WHOLE array (core.py:717).
+    Complex (or real) array of any shape in, complex128 (float64 for real input) array of the same shape out.
+    """
+    x = np.asarray(x)
+    host = np.ascontiguousarray(x.astype(np.complex128))
+    if host.size == 0:
+        return host if np.iscomplexobj(x) else host.real
+    torch = _cabi.require_cuda()
+    lib = _cabi.lib()
+    st = _vp(_cabi.stream_ptr(torch))
+    d = torch.from_numpy(host.view(np.float64)).to("cuda")
+    d_ws = torch.empty(4096 * 8 + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (d_ws.data_ptr() + 255) // 256 * 256
+    _cabi.check(lib.ocb_pnorm_run(_ptr(d), host.size, _vp(ws_ptr), 4096 * 8, st), "ocb_pnorm_run")
+    out = d.cpu().numpy().view(np.complex128).reshape(x.shape)
+    return out if np.iscomplexobj(x) else out.real

@@ -236,3 +236,17 @@ extern "C" int ocb_cpr_bps_run(const void* x_dev, int x_dtype, int64_t L, int nM
     OCB_LAUNCH(k_pnorm_scale, g, 256, 0, st, (double2*)y_out, n, partials, gp);
     return 0;
 }
+
+// pnorm (optic/dsp/core.py:702-717): x / sqrt(mean(|x|^2)) over the WHOLE array, in place, complex128.
+// workspace: >= 4096 doubles of reduction scratch.
+extern "C" int ocb_pnorm_run(void* x_dev, int64_t n, void* workspace, int64_t workspace_bytes, void* stream) {
+    OCB_REQUIRE(x_dev && workspace && n > 0, "pnorm_run: bad argument");
+    OCB_REQUIRE(workspace_bytes >= 4096 * 8, "pnorm_run: workspace too small (4096 doubles)");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* partials = (double*)workspace;
+    const int g = grid_for(n, 256, 2);
+    const int gp = g < 1024 ? g : 1024;
+    OCB_LAUNCH(k_power_partials, gp, 256, 0, st, (const double2*)x_dev, n, partials);
+    OCB_LAUNCH(k_pnorm_scale, g, 256, 0, st, (double2*)x_dev, n, partials, gp);
+    return 0;
+}

@@ -66,3 +66,16 @@ def test_decimate_golden(g):
     assert np.array_equal(y.astype(np.complex64), g["dec_4_2"].astype(np.complex64))
     with pytest.raises(ValueError):
         decimate(s[:4001], Bag(SpSin=4, SpSout=2))
+
+
+def test_pnorm_vs_oracle():
+    from opticommpy_b200.core import pnorm
+    from oracle import rxdsp_oracle as ro
+    rng = np.random.default_rng(3)
+    x = 3.7 * (rng.normal(size=(100001, 2)) + 1j * rng.normal(size=(100001, 2)))
+    y = pnorm(x)
+    assert y.shape == x.shape and y.dtype == np.complex128
+    assert rel(y, ro.pnorm(x)) < 1e-14
+    assert np.mean(np.abs(y) ** 2) == pytest.approx(1.0, rel=1e-13)
+    r = pnorm(x.real.copy()[:, 0])
+    assert r.dtype == np.float64 and np.mean(r ** 2) == pytest.approx(1.0, rel=1e-13)
