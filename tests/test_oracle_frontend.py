@@ -38,3 +38,28 @@ def test_decimate_matches_reference(g):
     assert y.shape == g["dec_16_1_1d"].shape and np.array_equal(y, g["dec_16_1_1d"])
     y, _ = fe.decimate(s[:4000], 4, 2)
     assert np.array_equal(y, g["dec_4_2"])
+
+
+@pytest.mark.parametrize("K", [1, 2, 7, 64, 257])
+def test_fir_oracle_equals_scipy_same_mode(K):
+    """Independent of the golden file: the oracle's centred slice is scipy's mode='same' for any filter length."""
+    from scipy import signal
+    rng = np.random.default_rng(K)
+    x = rng.normal(size=(1000, 2)) + 1j * rng.normal(size=(1000, 2))
+    h = rng.normal(size=K) + 1j * rng.normal(size=K)
+    ref = np.stack([signal.fftconvolve(x[:, n], h, mode="same") for n in range(2)], axis=1)
+    assert rel(fe.fir_filter(h, x), ref) < 1e-12
+
+
+def test_decimate_oracle_picks_the_eye_opening():
+    """Triangular transitions at 8 SpS peak at one phase per symbol; after a circular shift by 3 samples the
+    maximum-variance phase moves by 3 and the decimated sequence is the symbol sequence again."""
+    rng = np.random.default_rng(1)
+    lv = np.array([-3.0, -1.0, 1.0, 3.0])
+    sym = rng.choice(lv, size=500) + 1j * rng.choice(lv, size=500)
+    tri = np.convolve(np.repeat(sym, 8), np.ones(8) / 8)[: 8 * 500]   # full-amplitude sample at phase 7 of every symbol
+    y0, d0 = fe.decimate(tri, 8, 1)
+    assert d0 == [7] and np.allclose(y0, sym, atol=1e-12)
+    y3, d3 = fe.decimate(np.roll(tri, 3), 8, 1)
+    assert d3 == [(7 + 3) % 8]
+    assert np.allclose(y3[1:], sym[:-1], atol=1e-12)   # phase 2 of symbol slot k holds symbol k-1

@@ -35,3 +35,20 @@ def test_rls_oracle_matches_reference(g, tag):
     assert rel(err[:, :n], g[f"{tag}_err"].real[:, :n]) < 2e-3
     if CASES[tag].get("storeCoeff"):
         assert Hiter.shape == g[f"{tag}_Hiter"].shape and rel(Hiter, g[f"{tag}_Hiter"]) < 2e-4
+
+
+def test_rls_oracle_converges_on_a_clean_channel():
+    """Sanity of the restated recursion itself: on a noiseless 2x2 mixing channel RLS drives the error to ~0
+    within a few hundred symbols, and decision-directed RLS started from those taps keeps it there."""
+    from opticommpy_b200.modulation import grayMapping
+    rng = np.random.default_rng(8)
+    c = grayMapping(4, "qam").astype(np.complex128)
+    c /= np.sqrt(np.mean(np.abs(c) ** 2))
+    sym = c[rng.integers(0, 4, size=(1200, 2))]
+    th = 0.6
+    x = np.repeat(sym, 2, axis=0) @ np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]]).T
+    y, H, _, err, _ = ro.mimo_adapt_equalizer(x, sym, grayMapping(4, "qam"), nTaps=5, SpS=2, alg=("rls", "dd-rls"),
+                                              mu=(1e-3, 1e-3), L=(600, 600), lambdaRLS=0.99)
+    assert np.max(err[:, 300:600]) < 1e-4      # trained stage (squared error; the input is rounded to complex64)
+    assert np.max(err[:, 700:1200]) < 1e-4     # decision-directed stage stays locked
+    assert np.max(np.abs(y[300:1200] - sym[300:1200])) < 1e-2
