@@ -18,7 +18,7 @@ sys.path.insert(0, os.environ.get("OPTICOMMPY_REF", "/root/reference"))
 
 import numpy as np  # noqa: E402
 
-from optic.dsp.core import decimate, firFilter, pulseShape  # noqa: E402
+from optic.dsp.core import decimate, firFilter, pulseShape, symbolSync  # noqa: E402
 from optic.utils import parameters  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_frontend.npz")
@@ -64,6 +64,21 @@ p.SpSout = 1
 G["dec_16_1_1d"] = decimate(sig[:, 1], p)
 p.SpSin, p.SpSout = 4, 2
 G["dec_4_2"] = decimate(sig[: 4 * 1000], p)
+
+# symbolSync: swapped, delayed (and, for 'real' mode, rotated / conjugated) transmit sequences against a noisy
+# 2-SpS received signal
+nss = 1200
+c16 = np.array([a + 1j * b for a in (-3, -1, 1, 3) for b in (-3, -1, 1, 3)]) / np.sqrt(10)
+txs = c16[rng.integers(0, 16, size=(nss, 2))]
+rxs = np.repeat(txs, 2, axis=0)
+rxs += 0.05 * (rng.normal(size=rxs.shape) + 1j * rng.normal(size=rxs.shape))
+tx_amp = np.stack([np.roll(txs[:, 1], 7), np.roll(txs[:, 0], -11)], axis=1)           # swapped + delayed
+G["sync_rx"], G["sync_tx_amp"] = rxs, tx_amp
+G["sync_amp"] = symbolSync(rxs.copy(), tx_amp.copy(), 2, "amp")
+tx_real = np.stack([1j * np.roll(txs[:, 1], 5), np.conj(np.roll(txs[:, 0], -3))], axis=1)  # + rotation / conjugation
+G["sync_tx_real"] = tx_real
+G["sync_real"] = symbolSync(rxs.copy(), tx_real.copy(), 2, "real")
+G["sync_amp_1d"] = symbolSync(rxs[:, 0].copy(), np.roll(txs[:, 0], 9), 2, "amp")
 
 np.savez_compressed(OUT, **G)
 print({k: (v.shape, v.dtype) for k, v in G.items()})

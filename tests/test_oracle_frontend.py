@@ -63,3 +63,14 @@ def test_decimate_oracle_picks_the_eye_opening():
     y3, d3 = fe.decimate(np.roll(tri, 3), 8, 1)
     assert d3 == [(7 + 3) % 8]
     assert np.allclose(y3[1:], sym[:-1], atol=1e-12)   # phase 2 of symbol slot k holds symbol k-1
+
+
+def test_symbol_sync_matches_reference(g):
+    """symbolSync (core.py:552-675) restated in the oracle — test infrastructure for the next §8f row."""
+    y = fe.symbol_sync(g["sync_rx"], g["sync_tx_amp"], 2, "amp")
+    assert np.array_equal(y, g["sync_amp"])
+    y = fe.symbol_sync(g["sync_rx"], g["sync_tx_real"], 2, "real")
+    assert np.allclose(y, g["sync_real"], atol=1e-12)
+    tx0 = np.roll(g["sync_tx_amp"][:, 1], 11)          # the generator built column 1 as roll(tx0, -11)
+    y = fe.symbol_sync(g["sync_rx"][:, 0], np.roll(tx0, 9), 2, "amp")
+    assert y.shape == g["sync_amp_1d"].shape and np.array_equal(y, g["sync_amp_1d"])
