@@ -10,7 +10,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libopticomm_b200.so")
+# OCB_LIB: another build of the same library (A/B experiments, e.g. tools/drift_experiment.py)
+LIB_PATH = os.environ.get("OCB_LIB") or os.path.join(_HERE, "libopticomm_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "opticomm_b200.h")
 
 OCB_C64, OCB_C128 = 0, 1

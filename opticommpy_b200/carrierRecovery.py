@@ -12,17 +12,11 @@ import ctypes as C
 import logging as logg
 
 import numpy as np
-from numpy.fft import fft, fftfreq, fftshift
 
 from . import _cabi
 from .modulation import grayMapping
 
 _vp = C.c_void_p
-
-
-def _pnorm(x):
-    """Normalise the average power of ``x`` over all entries (optic/dsp/core.py:702-717)."""
-    return x / np.sqrt(np.mean(x * np.conj(x)).real)
 
 
 def bps(sigIn, N, constSymb, B, returnIndex=False):
@@ -69,21 +63,6 @@ def bps(sigIn, N, constSymb, B, returnIndex=False):
     if returnIndex:
         return phaseEst, d_idx.cpu().numpy()
     return phaseEst
-
-
-def fourthPowerFOE(sigIn, Fs, M=4):
-    """4th-power frequency-offset estimate/compensation (carrierRecovery.py:333-371), host side."""
-    Nfft = sigIn.shape[0]
-    f = fftshift(Fs * fftfreq(Nfft))
-    nModes = sigIn.shape[1]
-    sigOut = sigIn.copy()
-    t = np.arange(0, sigOut.shape[0]) * 1 / Fs
-    fo = np.zeros(nModes)
-    for n in range(nModes):
-        spec = 10 * np.log10(np.abs(fftshift(fft(sigIn[:, n] ** M))))
-        fo[n] = f[np.argmax(spec)] / M
-        sigOut[:, n] = sigIn[:, n] * np.exp(-1j * 2 * np.pi * fo[n] * t)
-    return sigOut, fo
 
 
 def cpr(sigIn, param=None, symbTx=None):

@@ -151,18 +151,25 @@ def manakov_rows_device(rows, param, direction=+1, noise_rows=None):
     if direction > 0 and param.amp == "edfa":
         gain_lin, noise_var = _edfa_numbers(param.alpha * param.Lspan, param.NF, param.Fc, param.Fs)
     noise_mode = _cabi.NOISE_INJECTED if noise_rows is not None else _cabi.NOISE_PHILOX
-    key = int(getattr(param, "seed", None) or 0) & 0xFFFFFFFFFFFFFFFF
+    # Noise of this entry: ``noise_rows`` (a (K, N) complex64 CUDA tensor) reproduces the reference's seeded
+    # CPU semantics (one realisation shared by x, y and every span); otherwise on-device Philox streams keyed by
+    # ``param.seed`` — and, like manakovSSF, by a fresh random key when the seed is None, so that Monte-Carlo
+    # calls without a seed are independent.  ``noiseRNG`` does not apply here (no host-side MT19937 stream).
+    seed = getattr(param, "seed", None)
+    key = (int(seed) if seed is not None
+           else int(np.random.SeedSequence().generate_state(1, np.uint64)[0])) & 0xFFFFFFFFFFFFFFFF
     Nspans = int(np.floor(param.Ltotal / param.Lspan))
     q = _manakov_params(param, direction, Nspans, 0, alpha_lin=alpha_lin, beta2=beta2, Fs=param.Fs,
                         noise_var=noise_var, gain_lin=gain_lin, noise_mode=noise_mode, key=key)
     stats = _cabi.ManakovStats()
-    plan = _engine.get_plan(N, R, rows.device.index)
-    _cabi.check(
-        lib.ocb_manakov_run(plan.handle, C.c_void_p(rows.data_ptr()), C.byref(q),
-                            C.c_void_p(noise_rows.data_ptr()) if noise_rows is not None else None,
-                            None, None, C.byref(stats), C.c_void_p(_cabi.stream_ptr(torch))),
-        "ocb_manakov_run",
-    )
+    with torch.cuda.device(rows.device):  # plan, kernels and stream all belong to the device that owns `rows`
+        plan = _engine.get_plan(N, R, rows.device.index)
+        _cabi.check(
+            lib.ocb_manakov_run(plan.handle, C.c_void_p(rows.data_ptr()), C.byref(q),
+                                C.c_void_p(noise_rows.data_ptr()) if noise_rows is not None else None,
+                                None, None, C.byref(stats), C.c_void_p(_cabi.stream_ptr(torch))),
+            "ocb_manakov_run",
+        )
     return {"steps": int(stats.steps), "iterations": int(stats.iterations), "nonconverged": int(stats.nonconverged),
             "last_lim": float(stats.last_lim)}
 

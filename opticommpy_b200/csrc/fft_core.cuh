@@ -21,22 +21,42 @@ __device__ __forceinline__ void static_for(F&& f) {
     }
 }
 
-// cos(2 pi k / 32), k = 0..8, correctly rounded to float
-__host__ __device__ constexpr float cos32_q(int k) {
-    constexpr float t[9] = {1.0f,           0.98078528040323f, 0.92387953251129f,
-                            0.83146961230255f, 0.70710678118655f, 0.55557023301960f,
-                            0.38268343236509f, 0.19509032201613f, 0.0f};
+// Double-single twiddles (OCB_DS, default on).  Every twiddle factor w is kept as an unevaluated sum hi + lo of two
+// floats (lo = float(w - hi), about 2^-24 |w|) and a product x*w is evaluated as x*hi + x*lo.  The FIXED rounding
+// error of a float twiddle (~3e-8 relative) acts on nearly the same field in every split-step, so it accumulates
+// linearly with the step count (measured 2.2e-7 per step in round 1); with the lo term the fixed error drops to
+// ~1e-15 and what is left is the data-dependent rounding of the float arithmetic, which grows like a random walk.
+#ifndef OCB_DS
+#define OCB_DS 1
+#endif
+constexpr bool kDS = (OCB_DS != 0);
+
+// cos(2 pi k / 32), k = 0..8, to double precision
+__host__ __device__ constexpr double cos32_qd(int k) {
+    constexpr double t[9] = {1.0,
+                             0.98078528040323044912618223613424,
+                             0.92387953251128675612818318939679,
+                             0.83146961230254523707878837761791,
+                             0.70710678118654752440084436210485,
+                             0.55557023301960222474283081394853,
+                             0.38268343236508977172845998403040,
+                             0.19509032201612826784828486847702,
+                             0.0};
     return t[k];
 }
 // cos / sin of 2 pi k / 32 for any integer k (symmetry-reduced to the table above)
-__host__ __device__ constexpr float cos32(int k) {
+__host__ __device__ constexpr double cos32d(int k) {
     k = ((k % 32) + 32) % 32;
-    if (k <= 8) return cos32_q(k);
-    if (k <= 16) return -cos32_q(16 - k);
-    if (k <= 24) return -cos32_q(k - 16);
-    return cos32_q(32 - k);
+    if (k <= 8) return cos32_qd(k);
+    if (k <= 16) return -cos32_qd(16 - k);
+    if (k <= 24) return -cos32_qd(k - 16);
+    return cos32_qd(32 - k);
 }
-__host__ __device__ constexpr float sin32(int k) { return cos32(k - 8); }
+__host__ __device__ constexpr double sin32d(int k) { return cos32d(k - 8); }
+__host__ __device__ constexpr float hi_part(double v) { return (float)v; }
+__host__ __device__ constexpr float lo_part(double v) { return (float)(v - (double)(float)v); }
+__host__ __device__ constexpr float cos32(int k) { return hi_part(cos32d(k)); }
+__host__ __device__ constexpr float sin32(int k) { return hi_part(sin32d(k)); }
 
 __host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 template <int R>
@@ -44,6 +64,24 @@ __host__ __device__ constexpr int brev(int k) {
     int r = 0;
     for (int b = 0; b < ilog2(R); ++b) r |= ((k >> b) & 1) << (ilog2(R) - 1 - b);
     return r;
+}
+
+// a * (h + l) and a * conj(h + l) for a double-single factor (l is ignored when OCB_DS = 0)
+__device__ __forceinline__ float2 cmul_ds(float2 a, float2 h, float2 l) {
+    if constexpr (kDS) {
+        return make_float2(fmaf(a.x, h.x, fmaf(-a.y, h.y, fmaf(a.x, l.x, -a.y * l.y))),
+                           fmaf(a.x, h.y, fmaf(a.y, h.x, fmaf(a.x, l.y, a.y * l.x))));
+    } else {
+        return cmul(a, h);
+    }
+}
+__device__ __forceinline__ float2 cmul_conj_ds(float2 a, float2 h, float2 l) {
+    if constexpr (kDS) {
+        return make_float2(fmaf(a.x, h.x, fmaf(a.y, h.y, fmaf(a.x, l.x, a.y * l.y))),
+                           fmaf(a.y, h.x, fmaf(-a.x, h.y, fmaf(a.y, l.x, -a.x * l.y))));
+    } else {
+        return cmul_conj(a, h);
+    }
 }
 
 // t * exp(DIR * 2 pi i * J / LEN), J and LEN compile-time (trivial factors cost no multiply)
@@ -58,6 +96,19 @@ __device__ __forceinline__ float2 twiddle_mul(float2 t) {
         return make_float2(-t.x, -t.y);
     } else if constexpr (K == 24) {
         return DIR > 0 ? make_float2(t.y, -t.x) : make_float2(-t.y, t.x);
+    } else if constexpr (kDS && (K == 4 || K == 12)) {
+        // exp(DIR i pi/4) = r (1 + DIR i), exp(DIR 3 i pi/4) = r (-1 + DIR i), r = sqrt(1/2) = rh + rl
+        constexpr float rh = hi_part(cos32d(4)), rl = lo_part(cos32d(4));
+        constexpr float d = (DIR > 0 ? 1.f : -1.f);
+        const float a = (K == 4) ? (t.x - d * t.y) : (-t.x - d * t.y);
+        const float b = (K == 4) ? (t.y + d * t.x) : (-t.y + d * t.x);
+        return make_float2(fmaf(a, rh, a * rl), fmaf(b, rh, b * rl));
+    } else if constexpr (kDS) {
+        constexpr float d = (DIR > 0 ? 1.f : -1.f);
+        constexpr float c = hi_part(cos32d(K)), cl = lo_part(cos32d(K));
+        constexpr float s = d * hi_part(sin32d(K)), sl = d * lo_part(sin32d(K));
+        return make_float2(fmaf(t.x, c, fmaf(-t.y, s, fmaf(t.x, cl, -t.y * sl))),
+                           fmaf(t.x, s, fmaf(t.y, c, fmaf(t.x, sl, t.y * cl))));
     } else {
         constexpr float c = cos32(K), s = (DIR > 0 ? 1.f : -1.f) * sin32(K);
         return make_float2(fmaf(t.x, c, -t.y * s), fmaf(t.x, s, t.y * c));
@@ -121,16 +172,17 @@ struct Coop {
 
 // HALF = true: the exchange runs in two rounds (real parts, then imaginary parts) through ONE planar array
 // (xr; xi unused), which halves the shared-memory footprint at the price of two more barriers per transform.
+// tw_lo: the lo parts of the table, same layout (read only when OCB_DS = 1)
 template <int Q, int CP, int PAD, bool HALF = false, typename SyncF>
 __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi, const float2* __restrict__ tw,
-                                                 int q, int c, SyncF&& sync) {
+                                                 const float2* __restrict__ tw_lo, int q, int c, SyncF&& sync) {
     constexpr int G = 32 / Q, STR = Q * CP + PAD;
     fft_dif<32, -1>(v);  // v[brev5(ka)] = Z[ka]
     if constexpr (!HALF) {
         static_for<0, 32>([&](auto kk) {
             constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
             float2 z = v[SLOT];
-            if constexpr (KA != 0) z = cmul(z, tw[KA * Q + q]);
+            if constexpr (KA != 0) z = cmul_ds(z, tw[KA * Q + q], kDS ? tw_lo[KA * Q + q] : float2{});
             xr[KA * STR + q * CP + c] = z.x;
             xi[KA * STR + q * CP + c] = z.y;
         });
@@ -147,7 +199,7 @@ __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi
     } else {
         static_for<0, 32>([&](auto kk) {
             constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
-            if constexpr (KA != 0) v[SLOT] = cmul(v[SLOT], tw[KA * Q + q]);
+            if constexpr (KA != 0) v[SLOT] = cmul_ds(v[SLOT], tw[KA * Q + q], kDS ? tw_lo[KA * Q + q] : float2{});
             xr[KA * STR + q * CP + c] = v[SLOT].x;
         });
         sync();
@@ -175,13 +227,12 @@ __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi
     static_for<0, G>([&](auto gg) { fft_dif<Q, -1>(v + decltype(gg)::value * Q); });
 }
 
-// twt: the transposed copy of the table, entry [J][ka] (defaults to tw + 32*Q; for Q = 32 the table is
-// symmetric and twt may alias tw).
+// twt / twt_lo: the TRANSPOSED copy of the table (hi and lo parts), entry [J][ka]; for Q = 32 the table is
+// symmetric and the transposed copy is the table itself.
 template <int Q, int CP, int PAD, bool HALF = false, typename SyncF>
-__device__ __forceinline__ void coop_fft_inverse(float2* v, float* xr, float* xi, const float2* __restrict__ tw,
-                                                 int q, int c, SyncF&& sync, const float2* __restrict__ twt = nullptr) {
+__device__ __forceinline__ void coop_fft_inverse(float2* v, float* xr, float* xi, const float2* __restrict__ twt,
+                                                 const float2* __restrict__ twt_lo, int q, int c, SyncF&& sync) {
     constexpr int G = 32 / Q, STR = Q * CP + PAD;
-    if (twt == nullptr) twt = tw + 32 * Q;
     static_for<0, G>([&](auto gg) { fft_dit<Q, +1>(v + decltype(gg)::value * Q); });  // over kq -> q'
     static_for<0, G>([&](auto gg) {
         constexpr int GI = decltype(gg)::value;
@@ -189,8 +240,7 @@ __device__ __forceinline__ void coop_fft_inverse(float2* v, float* xr, float* xi
         static_for<0, Q>([&](auto jj) {
             constexpr int J = decltype(jj)::value;  // q'
             // transposed copy of the table: entry [J][ka], so that lanes (ka) are contiguous
-            const float2 w = twt[J * 32 + ka];
-            const float2 z = cmul_conj(v[GI * Q + J], w);  // conj twiddle for the inverse
+            const float2 z = cmul_conj_ds(v[GI * Q + J], twt[J * 32 + ka], kDS ? twt_lo[J * 32 + ka] : float2{});  // conj twiddle
             v[GI * Q + J] = z;
             xr[ka * STR + J * CP + c] = z.x;
             if constexpr (!HALF) xi[ka * STR + J * CP + c] = z.y;

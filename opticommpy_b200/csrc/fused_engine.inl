@@ -11,6 +11,19 @@ bool pdl_enabled() {
     return !(v && atoi(v) == 0);
 }
 
+// One-time per-DEVICE setup (function attributes and device limits are per device/context, and one process may
+// drive several GPUs): true the first time `slot` is seen on the current device.
+enum OnceSlot { ONCE_L2_LIMIT = 0, ONCE_FREQ_BASE = 1, ONCE_SLOTS = 16 };
+bool first_time_on_device(int slot) {
+    static bool done[ONCE_SLOTS][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& d = done[slot][dev & 63];
+    if (d) return false;
+    d = true;
+    return true;
+}
+
 template <int Q1, int NP, int MODE>
 int launch_time_t(const TimeArgs& a, cudaStream_t st) {
     const int tasks_per_cta = 64 / Q1;
@@ -35,12 +48,9 @@ int freq_c() {
 template <int Q2, int C>
 int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP, const long long* flag,
                   long long step_id, const long long* need_flag, long long need_id, cudaStream_t st) {
-    static bool configured = false;
     const size_t smem = FreqCfg<Q2, C>::SMEM_BYTES;
-    if (!configured) {
+    if (first_time_on_device(ONCE_FREQ_BASE + fft::ilog2(Q2) + (C == 16 ? 6 : 0)))
         OCB_CUDA(cudaFuncSetAttribute(k_freq<Q2, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     OCB_LAUNCH_PDL((k_freq<Q2, C>), NP * N1 / C, Q2 * C, smem, st, pdl_enabled(), W, LP, tw, N1, flag, step_id, need_flag, need_id);
     return 0;
 }
@@ -56,11 +66,7 @@ int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, i
     return fail("fused engine: unsupported N2", __FILE__, __LINE__);
 }
 int launch_linop_perm(ocb_ssfm_plan* p, float2* LP, double a, double b, double Fs, double h, double scale,
-                      cudaStream_t st, bool split = false) {
-    if (split) {
-        OCB_LAUNCH(k_tab_linop_perm_s, grid_for(p->N, 256, 1), 256, 0, st, LP, kFreqC, p->N, a, b, Fs, h, scale);
-        return 0;
-    }
+                      cudaStream_t st) {
     OCB_LAUNCH(k_tab_linop_perm, grid_for(p->N, 256, 1), 256, 0, st, LP, p->q1, p->q2,
                (p->q2 == 32 ? freq_c() : kFreqC), p->N, a, b, Fs, h, scale);
     return 0;
@@ -86,58 +92,6 @@ int fused_init_tables(ocb_ssfm_plan* p, cudaStream_t st) {
     return 0;
 }
 
-// pair-split kernels (N1 = N2 = 1024, both polarisations)
-template <int MODE>
-int launch_time_s(const TimeArgs& a, cudaStream_t st) {
-    OCB_LAUNCH((k_time_s<MODE>), a.N2, 128, 0, st, a);
-    return 0;
-}
-int launch_freq_s(float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st,
-                  const long long* flag = nullptr, long long step_id = 0) {
-    static bool configured = false;
-    constexpr int C = kFreqC;
-    const size_t smem = (size_t)2 * 32 * (32 * C + 16) * sizeof(float);
-    if (!configured) {
-        OCB_CUDA(cudaFuncSetAttribute(k_freq_s<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    OCB_LAUNCH((k_freq_s<C>), NP * N1 / C, 64 * C, smem, st, W, LP, tw, N1, flag, step_id);
-    return 0;
-}
-
-// persistent pipelined time kernels (N1 = 1024, both polarisations): fused_pipe_kernels.cuh
-struct PipeKnobs {
-    bool time_on;     // OCB_TPIPE=0 falls back to the one-wave k_time
-    bool stage_h;     // OCB_TPIPE_SH: E_hd / P_ch rows staged through shared memory too
-    int ctas_iter, ctas_first, ctas_fwd;  // grid sizes (0: default = resident CTAs x 148)
-};
-PipeKnobs read_pipe_knobs() {
-    auto geti = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
-    PipeKnobs k;
-    k.time_on = geti("OCB_TPIPE", 0) != 0;  // measured slower than the one-wave kernels (6 warps per SM): off by default
-    k.stage_h = geti("OCB_TPIPE_SH", 1) != 0;
-    k.ctas_iter = geti("OCB_TPIPE_GRID_ITER", 0);
-    k.ctas_first = geti("OCB_TPIPE_GRID_FIRST", 0);
-    k.ctas_fwd = geti("OCB_TPIPE_GRID_FWD", 0);
-    return k;
-}
-template <int MODE, bool SH>
-int launch_time_p(const TimeArgs& a, int grid, cudaStream_t st) {
-    using Cfg = TimePipeCfg<MODE, SH>;
-    static bool configured = false;
-    if (!configured) {
-        OCB_CUDA(cudaFuncSetAttribute(k_time_p<MODE, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
-    if (grid <= 0) {
-        const int resident = (227 * 1024) / (Cfg::SMEM_BYTES + 2048);  // 1 KB reserved per CTA + static reduction scratch
-        grid = kNumSMs * resident;
-    }
-    if (grid > a.N2) grid = a.N2;
-    OCB_LAUNCH((k_time_p<MODE, SH>), grid, 64, Cfg::SMEM_BYTES, st, a);
-    return 0;
-}
-
 TimeArgs time_base(ocb_ssfm_plan* p) {
     TimeArgs a{};
     a.tw = p->tw1; a.tabV = p->tabV; a.tabU = p->tabU;
@@ -157,9 +111,6 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
     const double a = -dir * q->alpha_lin / 2.0, b = dir * q->beta2 / 2.0;
     const size_t field_bytes = (size_t)R * N * sizeof(float2);
     if (fused_init_tables(p, st)) return 1;
-    const bool split = p->split;
-    const PipeKnobs pk = read_pipe_knobs();
-    const bool tpipe = pk.time_on && !split && p->q1 == 32;
     // One field buffer: k_time<TM_ITER> replaces the previous iterate by the new one in place, which keeps
     // the per-iteration working set (W, E_c, E_hd, P_ch, operator table = 60 MB at N = 2^20) inside L2.
     float2* bufs[3] = {p->A, p->A, p->A};
@@ -175,10 +126,17 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
     bool chained = false;           // first half + iteration 0 of the coming step are already enqueued
     unsigned long long chained_seq = 0;
 
-    // keep the operator tables (read by every k_freq launch) resident in L2
+    // keep the operator tables (read by every k_freq launch) resident in L2 for the duration of this call; the
+    // caller's stream gets its previous access-policy window back on every return path
+    struct WindowGuard {
+        cudaStream_t st; cudaStreamAttrValue old{}; bool have = false;
+        ~WindowGuard() { if (have) { cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &old); cudaGetLastError(); } }
+    } wguard;
+    wguard.st = st;
+    wguard.have = cudaStreamGetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &wguard.old) == cudaSuccess;
+    cudaGetLastError();
     {
-        static bool limit_set = false;
-        if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 32u << 20); limit_set = true; }
+        if (first_time_on_device(ONCE_L2_LIMIT)) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 32u << 20);
         cudaStreamAttrValue attr{};
         attr.accessPolicyWindow.base_ptr = p->T1;
         attr.accessPolicyWindow.num_bytes = (size_t)((char*)p->Pch - (char*)p->T1);  // T1 and T2
@@ -217,7 +175,7 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                 hz_ = q->hz;
             }
             if (!(table_h == hz_)) {
-                if (launch_linop_perm(p, LP, a, b, q->Fs, hz_ / 2.0, 1.0 / (double)N, st, split)) return 1;
+                if (launch_linop_perm(p, LP, a, b, q->Fs, hz_ / 2.0, 1.0 / (double)N, st)) return 1;
                 table_h = hz_;
             }
             // ---- one SSFM step --------------------------------------------------------------------------
@@ -251,14 +209,10 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                                     long long need_id) -> int {
                 {
                     ProfScope ps(p, 2, st);
-                    if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st, p->conv_flag, sid)
-                              : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, p->conv_flag, sid, need, need_id)) return 1;
+                    if (launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, p->conv_flag, sid, need, need_id)) return 1;
                 }
                 ProfScope ps(p, 0, st);
                 const TimeArgs ci = time_args_iter(sid, seq, final_pred, need, need_id);
-                if (tpipe) return pk.stage_h ? launch_time_p<TM_ITER, true>(ci, pk.ctas_iter, st)
-                                             : launch_time_p<TM_ITER, false>(ci, pk.ctas_iter, st);
-                if (split) return launch_time_s<TM_ITER>(ci, st);
                 return final_pred ? launch_time<2, TM_ITERF>(p->q1, ci, st) : launch_time<2, TM_ITER>(p->q1, ci, st);
             };
             // first half step from the frequency-side buffer (channels.py:409-410 after the forward time pass):
@@ -269,22 +223,19 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                     if (with_fwd) {
                         TimeArgs c0 = time_base(p);
                         c0.in = p->A; c0.out = Wb;
-                        if (tpipe ? launch_time_p<TM_FWD, false>(c0, pk.ctas_fwd, st)
-                                  : split ? launch_time_s<TM_FWD>(c0, st) : launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
+                        if (launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
                     }
-                    if (split ? launch_freq_s(Wb, LP, p->tw2, N1, R, st)
-                              : launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, nullptr, 0, need, need_id)) return 1;
+                    if (launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, nullptr, 0, need, need_id)) return 1;
                 }
                 ProfScope ps(p, 1, st);
                 TimeArgs c1 = time_base(p);
                 c1.in = Wb; c1.out = Wb; c1.aux0 = p->A; c1.aux1 = p->Ehd; c1.pch = p->Pch;
                 c1.cphi = cphi_first;
                 c1.need_flag = need; c1.need_id = need_id;
-                return tpipe ? launch_time_p<TM_FIRST, false>(c1, pk.ctas_first, st)
-                             : split ? launch_time_s<TM_FIRST>(c1, st) : launch_time<2, TM_FIRST>(p->q1, c1, st);
+                return launch_time<2, TM_FIRST>(p->q1, c1, st);
             };
 
-            const bool can_predict = predict && speculate && !split && !tpipe && !q->nlprMethod;
+            const bool can_predict = predict && speculate && !q->nlprMethod;
             int pred = (can_predict && last_iters >= 1 && last_iters <= q->maxIter) ? last_iters - 1 : -1;
             unsigned long long seq_cur;
             if (chained) {  // first half and iteration 0 of this step were enqueued behind the previous TM_ITERF
@@ -352,7 +303,7 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
         if (q->direction > 0) {  // channels.py:443-451
             if (q->amp_mode == OCB_AMP_EDFA) {
                 if (launch_amp(bufs[cur], R, N, sqrt(q->edfa_gain_lin), noiseT ? 0.0 : sqrt(q->edfa_noise_var / 2.0),
-                               noiseT, K, q->seed, amp_calls++, st)) return 1;
+                               noiseT, K, q->seed, amp_calls++, st, N1, 32 * p->q2)) return 1;
             } else if (q->amp_mode == OCB_AMP_IDEAL) {
                 if (launch_amp(bufs[cur], R, N, exp(q->alpha_lin / 2.0 * q->Lspan), 0.0, nullptr, 1, 0, 0, st)) return 1;
             }
@@ -406,10 +357,10 @@ static int fused_nlse_run(ocb_ssfm_plan* p, void* row_inout, const ocb_nlse_para
             if (launch_time<1, TM_INV>(p->q1, ci, st)) return 1;  // :232 + gain of :234/:236
             if (q->amp_mode == OCB_AMP_EDFA)  // noise only; the gain rode in the inverse time pass
                 if (launch_amp(E, 1, N, 1.0, inj ? 0.0 : sqrt(q->edfa_noise_var / 2.0), noiseT, 1, q->seed,
-                               (uint64_t)span, st)) return 1;
+                               (uint64_t)span, st, N1, 32 * p->q2)) return 1;
         } else if (q->amp_mode != OCB_AMP_NONE) {
             if (launch_amp(E, 1, N, gain, (q->amp_mode == OCB_AMP_EDFA && !inj) ? sqrt(q->edfa_noise_var / 2.0) : 0.0,
-                           noiseT, 1, q->seed, (uint64_t)span, st)) return 1;
+                           noiseT, 1, q->seed, (uint64_t)span, st, N1, 32 * p->q2)) return 1;
         }
     }
     if (launch_transpose(p, E, (float2*)row_inout, 1, false, 1.0f, st)) return 1;

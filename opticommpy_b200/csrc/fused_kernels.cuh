@@ -40,9 +40,9 @@ struct TimeArgs {
     float2* aux1;         // TM_FIRST: E_hd (written)       ; TM_ITER: new iterate (written)
     const float2* ehd;    // TM_ITER: E_hd (read)
     float* pch;           // TM_FIRST: written ; TM_ITER: read
-    const float2* tw;     // [32][Q1]  exp(-2 pi i q ka / N1)
-    const float2* tabV;   // [N2][32]  exp(-2 pi i n2 ka / N)
-    const float2* tabU;   // [N2][Q1]  exp(-2 pi i n2 32 kq / N)
+    const float2* tw;     // [32][Q1] exp(-2 pi i q ka / N1): hi, hi transposed, lo, lo transposed (32*Q1 entries each)
+    const float2* tabV;   // [N2][32]  exp(-2 pi i n2 ka / N), followed by the lo parts [N2][32]
+    const float2* tabU;   // [N2][Q1]  exp(-2 pi i n2 32 kq / N), followed by the lo parts [N2][Q1]
     double* partials;     // TM_ITER reduction scratch
     double* sums;
     unsigned* ticket;
@@ -81,10 +81,23 @@ k_time(const TimeArgs A) {
     const float2* tw = A.tw;  // 8 KB table, L1-resident
 
     float2 v[32];
-    float2 wV[G];
+    float2 wV[G], wVl[G];  // hi / lo parts (double-single twiddles, fft_core.cuh)
 #pragma unroll
-    for (int g = 0; g < G; ++g) wV[g] = __ldg(A.tabV + (int64_t)row * 32 + t * G + g);
+    for (int g = 0; g < G; ++g) {
+        wV[g] = __ldg(A.tabV + (int64_t)row * 32 + t * G + g);
+        wVl[g] = kDS ? __ldg(A.tabV + (int64_t)(A.N2 + row) * 32 + t * G + g) : float2{};
+    }
     const float2* Urow = A.tabU + (int64_t)row * Q1;
+    const float2* Urow_lo = A.tabU + (int64_t)(A.N2 + row) * Q1;
+    // inter-pass twiddle W_N^{n2 k1} = V[n2][ka] U[n2][kq], applied factor by factor
+    auto twiddle_fwd = [&](float2 x, int gi, int kq) {
+        if constexpr (kDS) return cmul_ds(cmul_ds(x, wV[gi], wVl[gi]), __ldg(Urow + kq), __ldg(Urow_lo + kq));
+        else return cmul(x, cmul(wV[gi], __ldg(Urow + kq)));
+    };
+    auto twiddle_inv = [&](float2 x, int gi, int kq) {
+        if constexpr (kDS) return cmul_conj_ds(cmul_conj_ds(x, wV[gi], wVl[gi]), __ldg(Urow + kq), __ldg(Urow_lo + kq));
+        else return cmul_conj(x, cmul(wV[gi], __ldg(Urow + kq)));
+    };
 
     // Secondary streams of the pointwise stage: start their HBM->L2 fetch now so that it overlaps the
     // W-row load and the inverse transform (one 128-byte line per lane and trip).
@@ -124,11 +137,10 @@ k_time(const TimeArgs A) {
             constexpr int GI = decltype(gg)::value;
             static_for<0, Q1>([&](auto kk) {
                 constexpr int KQ = decltype(kk)::value, SLOT = GI * Q1 + brev<Q1>(KQ);
-                const float2 w = cmul(wV[GI], __ldg(Urow + KQ));
-                v[SLOT] = cmul_conj(v[SLOT], w);  // conj twiddle W_N^{-n2 k1}
+                v[SLOT] = twiddle_inv(v[SLOT], GI, KQ);  // conj twiddle W_N^{-n2 k1}
             });
         });
-        coop_fft_inverse<Q1, 1, 1>(v, xr, xi, tw, t, 0, wsync);  // v[a'] = sample n1 = Q1*a' + t
+        coop_fft_inverse<Q1, 1, 1>(v, xr, xi, tw + 32 * Q1, tw + 96 * Q1, t, 0, wsync);  // v[a'] = sample n1 = Q1*a' + t
         __syncwarp();
     }
 
@@ -229,7 +241,7 @@ k_time(const TimeArgs A) {
     }
 
     // ---- leave: forward FFT over n1 + inter-pass twiddle -> W row ---------------------------------------
-    coop_fft_forward<Q1, 1, 1>(v, xr, xi, tw, t, 0, wsync);
+    coop_fft_forward<Q1, 1, 1>(v, xr, xi, tw, tw + 64 * Q1, t, 0, wsync);
     // TM_ITERF has just issued its 32 stores of the new iterate: post after the transform, when they have
     // drained, so that the ticket's fence does not wait for them
     if constexpr (MODE == TM_ITERF) my_ticket = block_reduce3_post(s_num, s_den, 0.f, A.partials, A.ticket);
@@ -239,8 +251,7 @@ k_time(const TimeArgs A) {
             constexpr int GI = decltype(gg)::value;
             static_for<0, Q1>([&](auto kk) {
                 constexpr int KQ = decltype(kk)::value, SLOT = GI * Q1 + brev<Q1>(KQ);
-                const float2 w = cmul(wV[GI], __ldg(Urow + KQ));
-                st_stream(dst + SLOT * Q1 + t, cmul(v[SLOT], w));
+                st_stream(dst + SLOT * Q1 + t, twiddle_fwd(v[SLOT], GI, KQ));
             });
         });
     }
@@ -258,7 +269,8 @@ k_time(const TimeArgs A) {
 template <int Q2, int C>
 struct FreqCfg {
     static constexpr int STR = Q2 * C + C;
-    static constexpr int TW_ENTRIES = (Q2 == 32 ? 1 : 2) * 32 * Q2;  // a 32 x 32 table is symmetric: one copy
+    static constexpr int TW_HALF = (Q2 == 32 ? 1 : 2) * 32 * Q2;  // a 32 x 32 table is symmetric: one copy
+    static constexpr int TW_ENTRIES = (fft::kDS ? 2 : 1) * TW_HALF;   // hi parts, then lo parts
     static constexpr int LP_ENTRIES = 32 * Q2 * C;
     static constexpr int SMEM_BYTES = 32 * STR * 4 + TW_ENTRIES * 8 + LP_ENTRIES * 8;
 };
@@ -294,8 +306,14 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
         for (int i = tid; i < Cfg::LP_ENTRIES * 8 / 16; i += NT) cp_async16_cg(dst + i * 16, src + i * 16);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int i = tid; i < Cfg::TW_ENTRIES; i += NT) tws[i] = __ldg(tw + i);
+    // global table: hi, hi transposed, lo, lo transposed (32*Q2 entries each)
+    for (int i = tid; i < Cfg::TW_HALF; i += NT) {
+        tws[i] = __ldg(tw + i);
+        if constexpr (kDS) tws[Cfg::TW_HALF + i] = __ldg(tw + 64 * Q2 + i);
+    }
     const float2* twt = (Q2 == 32) ? tws : tws + 32 * Q2;
+    const float2* tws_lo = tws + Cfg::TW_HALF;
+    const float2* twt_lo = (Q2 == 32) ? tws_lo : tws_lo + 32 * Q2;
 
     pdl_wait();  // W was written by the preceding time pass (programmatic dependent launch)
     pdl_launch_dependents();
@@ -309,11 +327,11 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
     for (int a = 0; a < 32; ++a) v[a] = ld_stream(base + (int64_t)(Q2 * a + q) * N1);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // twiddle table and operator slice staged
-    coop_fft_forward<Q2, C, C, true>(v, xr, nullptr, tws, q, c, bsync);
+    coop_fft_forward<Q2, C, C, true>(v, xr, nullptr, tws, tws_lo, q, c, bsync);
 #pragma unroll
     for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], lps[s * NT + tid]);
     __syncthreads();
-    coop_fft_inverse<Q2, C, C, true>(v, xr, nullptr, tws, q, c, bsync, twt);
+    coop_fft_inverse<Q2, C, C, true>(v, xr, nullptr, twt, twt_lo, q, c, bsync);
 #pragma unroll
     for (int a = 0; a < 32; ++a) st_stream(base + (int64_t)(Q2 * a + q) * N1, v[a]);
 }
@@ -339,30 +357,39 @@ __global__ void k_transpose(const float2* __restrict__ in, float2* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // Table builders (float64 math, rounded once to float32).
 // ------------------------------------------------------------------------------------------
-// tw[ka*Q + q] = exp(-2 pi i q ka / (32 Q)), followed by the transposed copy tw[32Q + q*32 + ka]
+// tw[ka*Q + q] = exp(-2 pi i q ka / (32 Q)): hi parts, hi parts transposed [q*32 + ka], lo parts, lo parts transposed
+// (32*Q entries each; the lo parts are what float rounding dropped, see fft_core.cuh)
 __global__ void k_tab_tw(float2* tw, int Q) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 32 * Q) return;
     const int ka = i / Q, q = i % Q;
     double s, c;
     sincospi(-2.0 * (double)(q * ka) / (double)(32 * Q), &s, &c);
-    tw[i] = make_float2((float)c, (float)s);
-    tw[32 * Q + q * 32 + ka] = make_float2((float)c, (float)s);
+    const float2 hi = make_float2((float)c, (float)s);
+    const float2 lo = make_float2((float)(c - (double)hi.x), (float)(s - (double)hi.y));
+    tw[i] = hi;
+    tw[32 * Q + q * 32 + ka] = hi;
+    tw[64 * Q + i] = lo;
+    tw[96 * Q + q * 32 + ka] = lo;
 }
-// V[n2*32 + ka] = exp(-2 pi i n2 ka / N) ; U[n2*Q1 + kq] = exp(-2 pi i n2 32 kq / N)
+// V[n2*32 + ka] = exp(-2 pi i n2 ka / N) ; U[n2*Q1 + kq] = exp(-2 pi i n2 32 kq / N); each followed by its lo parts
 __global__ void k_tab_inter(float2* V, float2* U, int N2, int Q1, int64_t N) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < (int64_t)N2 * 32) {
         const int64_t n2 = i / 32, ka = i % 32;
         double s, c;
         sincospi(-2.0 * (double)((n2 * ka) % N) / (double)N, &s, &c);
-        V[i] = make_float2((float)c, (float)s);
+        const float2 hi = make_float2((float)c, (float)s);
+        V[i] = hi;
+        V[(int64_t)N2 * 32 + i] = make_float2((float)(c - (double)hi.x), (float)(s - (double)hi.y));
     }
     if (i < (int64_t)N2 * Q1) {
         const int64_t n2 = i / Q1, kq = i % Q1;
         double s, c;
         sincospi(-2.0 * (double)((n2 * 32 * kq) % N) / (double)N, &s, &c);
-        U[i] = make_float2((float)c, (float)s);
+        const float2 hi = make_float2((float)c, (float)s);
+        U[i] = hi;
+        U[(int64_t)N2 * Q1 + i] = make_float2((float)(c - (double)hi.x), (float)(s - (double)hi.y));
     }
 }
 __host__ __device__ inline int brev_rt(int v, int bits) {

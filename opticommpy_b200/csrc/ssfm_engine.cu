@@ -13,8 +13,6 @@
 #include "../../include/opticomm_b200.h"
 #include "ssfm_kernels.cuh"
 #include "fused_kernels.cuh"
-#include "fused_split_kernels.cuh"
-#include "fused_pipe_kernels.cuh"
 
 using namespace ocb;
 
@@ -66,7 +64,6 @@ struct ocb_ssfm_plan {
     // fused four-step engine (power-of-two N = (32 q1) x (32 q2), single pol-pair): geometry + tables
     int engine = 0;       // OCB_ENGINE_*: 0 auto, 1 cuFFT, 2 fused
     bool fused_ok = false, fused_tables_ready = false;
-    bool split = false;   // pair-split kernels (16 samples per thread) for N1 = N2 = 1024, one pol-pair
     int q1 = 0, q2 = 0;
     float2 *tw1 = nullptr, *tw2 = nullptr, *tabV = nullptr, *tabU = nullptr;
     float2 *Cb = nullptr, *Nb = nullptr;  // third rotating field buffer, engine-layout noise copy
@@ -107,8 +104,9 @@ static bool fused_geometry(int64_t N, int* q1, int* q2) {
 }
 static int64_t fused_table_bytes(const ocb_ssfm_plan* p) {
     if (!p->fused_ok) return 0;
-    return align_up(2 * 32ll * p->q1 * 8, 256) + align_up(2 * 32ll * p->q2 * 8, 256) +
-           align_up(32ll * p->q2 * 32 * 8, 256) + align_up(32ll * p->q2 * p->q1 * 8, 256) +
+    // twiddle tables with their lo parts (double-single, fft_core.cuh): tw1, tw2 (hi, hi^T, lo, lo^T), V, U (hi, lo)
+    return align_up(4 * 32ll * p->q1 * 8, 256) + align_up(4 * 32ll * p->q2 * 8, 256) +
+           align_up(2 * 32ll * p->q2 * 32 * 8, 256) + align_up(2 * 32ll * p->q2 * p->q1 * 8, 256) +
            align_up((int64_t)p->rows * p->N * 8, 256) + align_up(p->N * 8, 256);
 }
 static int fused_manakov_run(ocb_ssfm_plan*, void*, const ocb_manakov_params*, const void*, const int32_t*, void*,
@@ -129,7 +127,6 @@ extern "C" int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out) {
     p->N = N;
     p->rows = rows;
     p->fused_ok = (rows == 1 || rows == 2) && fused_geometry(N, &p->q1, &p->q2);
-    p->split = p->fused_ok && rows == 2 && p->q1 == 32 && p->q2 == 32 && getenv("OCB_SPLIT") != nullptr;
     if (cufftCreate(&p->fft) != CUFFT_SUCCESS) { delete p; return fail("cufftCreate failed", __FILE__, __LINE__); }
     p->fft_ok = true;
     if (cufftSetAutoAllocation(p->fft, 0) != CUFFT_SUCCESS) { ocb_ssfm_plan_destroy(p); return fail("cufftSetAutoAllocation failed", __FILE__, __LINE__); }
@@ -185,10 +182,10 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
     p->fft_area = c; c += align_up((int64_t)p->fft_work, 256);
     if (p->fft_work > 0) OCB_CUFFT(cufftSetWorkArea(p->fft, p->fft_area));
     if (p->fused_ok) {
-        p->tw1 = (float2*)c; c += align_up(2 * 32ll * p->q1 * 8, 256);
-        p->tw2 = (float2*)c; c += align_up(2 * 32ll * p->q2 * 8, 256);
-        p->tabV = (float2*)c; c += align_up(32ll * p->q2 * 32 * 8, 256);
-        p->tabU = (float2*)c; c += align_up(32ll * p->q2 * p->q1 * 8, 256);
+        p->tw1 = (float2*)c; c += align_up(4 * 32ll * p->q1 * 8, 256);
+        p->tw2 = (float2*)c; c += align_up(4 * 32ll * p->q2 * 8, 256);
+        p->tabV = (float2*)c; c += align_up(2 * 32ll * p->q2 * 32 * 8, 256);
+        p->tabU = (float2*)c; c += align_up(2 * 32ll * p->q2 * p->q1 * 8, 256);
         p->Cb = (float2*)c; c += align_up((int64_t)p->rows * p->N * 8, 256);
         p->Nb = (float2*)c; c += align_up(p->N * 8, 256);
         p->fused_tables_ready = false;
@@ -312,9 +309,9 @@ static int launch_mul(ocb_ssfm_plan* p, float2* F, const float2* T, cudaStream_t
     return 0;
 }
 static int launch_amp(float2* E, int R, int64_t N, double g, double sigma, const float2* noise,
-                      int noise_rows, uint64_t seed, uint64_t stream_id, cudaStream_t st) {
+                      int noise_rows, uint64_t seed, uint64_t stream_id, cudaStream_t st, int tN1 = 0, int tN2 = 0) {
     OCB_LAUNCH(k_amp, grid_for((int64_t)R * N, 256, 2), 256, 0, st, E, R, N, (float)g, (float)sigma, noise,
-               noise_rows, seed, stream_id);
+               noise_rows, seed, stream_id, tN1, tN2);
     return 0;
 }
 static int nl_grid(const ocb_ssfm_plan* p, int64_t items) {
@@ -420,7 +417,8 @@ extern "C" int ocb_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_man
     OCB_REQUIRE(q->maxIter >= 1, "manakov_run: maxIter must be >= 1");
     OCB_REQUIRE(q->Lspan > 0, "manakov_run: Lspan must be > 0");
     OCB_REQUIRE(q->nlprMethod || q->hz > 0, "manakov_run: hz must be > 0");
-    if (q->nlprMethod) OCB_REQUIRE(q->gamma != 0.0, "manakov_run: nlprMethod=True with gamma=0 divides by zero (channels.py:394)");
+    // nlprMethod=True with gamma == 0: maxNlinPhaseRot / 0 = +inf in IEEE doubles, so the whole span is one linear
+    // step, exactly what the reference does (channels.py:394-397, with a RuntimeWarning)
     if (q->amp_mode == OCB_AMP_EDFA && q->direction == 1 && q->noise_mode == OCB_NOISE_INJECTED)
         OCB_REQUIRE(noise_dev != nullptr, "manakov_run: injected noise buffer missing");
     OCB_REQUIRE(q->n_save == 0 || (save_spans && save_dev), "manakov_run: snapshot buffers missing");

@@ -325,10 +325,12 @@ __device__ __forceinline__ float2 gauss_pair(uint32_t a, uint32_t b) {
 
 // E[r][n] = E[r][n]*g + noise     (gain-only when sigma == 0 and noise == nullptr)
 //   injected: noise[(r % noise_rows)][n]  — same realisation for x and y rows, every span
-//   philox  : CN(0, 2σ²) with counter (n, r, stream_id)
+//   philox  : CN(0, 2σ²) with counter (r*N + n, stream_id), n = NATURAL sample index: when the field is kept in
+//             the fused engine's transposed layout (position N1*n2 + n1 holds sample N2*n1 + n2; tN1 > 0) the
+//             counter is mapped back, so a seed gives the same realisation whichever engine runs the span
 __global__ void k_amp(float2* __restrict__ E, int R, int64_t N, float g, float sigma,
                       const float2* __restrict__ noise, int noise_rows, uint64_t seed,
-                      uint64_t stream_id) {
+                      uint64_t stream_id, int tN1, int tN2) {
     const int64_t total = (int64_t)R * N;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -339,7 +341,12 @@ __global__ void k_amp(float2* __restrict__ E, int R, int64_t N, float g, float s
             float2 w = __ldg(noise + (r % noise_rows) * N + n);
             e.x += w.x; e.y += w.y;
         } else if (sigma > 0.f) {
-            uint4 c = make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)stream_id,
+            int64_t ci = i;
+            if (tN1 > 0) {
+                const int64_t pos = i % N;
+                ci = (i - pos) + (int64_t)tN2 * (pos % tN1) + pos / tN1;
+            }
+            uint4 c = make_uint4((uint32_t)ci, (uint32_t)(ci >> 32), (uint32_t)stream_id,
                                  (uint32_t)(stream_id >> 32));
             uint4 rnd = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
             float2 w = gauss_pair(rnd.x, rnd.y);

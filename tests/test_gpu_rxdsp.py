@@ -145,3 +145,36 @@ def test_cpr_golden(api, golden):
     assert rel_l2(out, golden["cpr_foe_out"]) < 1e-12
     out1 = api.cpr(golden["bps_in"][:, 0], Bag(alg="bpsGPU", M=16, N=25, runFOE=False))
     assert out1.ndim == 1
+
+
+def test_cfg3_chain_vs_reference_golden(api):
+    """cfg3 geometry (BASELINE configs[2]): edc(800 km) -> 2x2 mimoAdaptEqualizer(CMA -> RDE, nTaps = 31, the case the
+    look-ahead kernel serves) -> cpr/bps(B = 64, window 25) on 2^17 symbols x 2 pol against the UNMODIFIED reference
+    (tests/golden/make_golden_cfg3.py).  Every stage is fed the previous stage's own output, like a user's chain.
+    Hard decisions after carrier recovery must be identical to the reference's."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from cfg3_signal import make_signal
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cfg3.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz")) as z:
+        c = z["const_qam16"]
+    c = c / np.sqrt(np.mean(np.abs(c) ** 2))
+    nsym = int(g["nsym"])
+    x, _ = make_signal(nsym, c, seed=int(g["seed"]))
+    y1 = api.edc(x, Bag(L=800, D=16, Fc=193.1e12, Fs=64e9, Rs=32e9))
+    assert rel_l2(y1[::8], g["edc_sub"]) < 1e-5
+    p = Bag(nTaps=31, SpS=2, M=16, constType="qam", alg=["cma", "rde"], mu=list(g["mu"]),
+            L=[int(0.2 * nsym), int(0.8 * nsym)], prgsBar=False, returnResults=True, prec=np.complex64)
+    y2, H, err, _ = api.eq(y1, p)
+    # 131072 adaptive updates in complex64 on both sides (numba fastmath vs CUDA, different summation order)
+    assert rel_l2(H, g["eq_H"]) < 1e-3
+    assert rel_l2(y2[::8], g["eq_y_sub"]) < 1e-3
+    y3, ph = api.cpr(y2, Bag(alg="bps", M=16, constType="qam", N=25, B=64, runFOE=False, returnPhases=True))
+    dec = lambda z: np.argmin(np.abs(z[..., None] - c), axis=-1).astype(np.uint8)
+    d = dec(y3)
+    mism = np.flatnonzero((d != g["cpr_dec"]).any(axis=1))
+    # identical decisions except where the reference's own sample sits on a decision boundary (none expected)
+    assert mism.size == 0, f"{mism.size} symbols decided differently, first at {mism[:5]}"
+    assert np.mean(np.isclose(ph, g["cpr_ph"], rtol=0, atol=1e-9)) > 0.999  # a discrete grid: equal unless a metric tie flips

@@ -153,3 +153,30 @@ def test_cpr_matches_reference(golden):
     out, ph = ro.cpr_bps(golden["cpr_foe_in"], golden["const_qam16"], N=35, B=64, runFOE=True, Ts=1 / 32e9)
     assert np.allclose(ph, golden["cpr_foe_ph"], atol=1e-12)
     assert rel_l2(out, golden["cpr_foe_out"]) < 1e-12
+
+
+def test_oracle_cfg3_chain_vs_reference():
+    """cfg3 geometry (edc 800 km -> CMA/RDE nTaps = 31 -> cpr/bps B = 64, 2^17 symbols x 2 pol): the oracle chain
+    against the unmodified reference's outputs (tests/golden/make_golden_cfg3.py); decisions identical."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from cfg3_signal import make_signal
+    from oracle import rxdsp_oracle as ro
+    with np.load(os.path.join(here, "golden", "ref_cfg3.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    with np.load(os.path.join(here, "golden", "ref_vectors.npz")) as z:
+        c0 = z["const_qam16"]
+    c = c0 / np.sqrt(np.mean(np.abs(c0) ** 2))
+    nsym = int(g["nsym"])
+    x, _ = make_signal(nsym, c, seed=int(g["seed"]))
+    y1 = ro.edc(x, 800, 16, 193.1e12, 64e9, 32e9)
+    assert rel_l2(y1[::8], g["edc_sub"]) < 1e-6
+    y2, H, _, err, _ = ro.mimo_adapt_equalizer(y1, None, c0, nTaps=31, SpS=2, alg=["cma", "rde"], mu=list(g["mu"]),
+                                              L=[int(0.2 * nsym), int(0.8 * nsym)])
+    assert rel_l2(H, g["eq_H"]) < 5e-5 and rel_l2(y2[::8], g["eq_y_sub"]) < 5e-5  # measured 4e-6 / 9e-7
+    out = ro.cpr_bps(y2, c0, N=25, B=64, runFOE=False)
+    y3 = out[0] if isinstance(out, tuple) else out
+    d = np.argmin(np.abs(y3[..., None] - c), axis=-1).astype(np.uint8)
+    assert not (d != g["cpr_dec"]).any()
