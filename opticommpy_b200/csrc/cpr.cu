@@ -9,6 +9,7 @@
 
 #include "../../include/opticomm_b200.h"
 #include "common.cuh"
+#include "plan_cache.cuh"
 
 using namespace ocb;
 
@@ -158,6 +159,18 @@ k_unwrap_apply(const int32_t* __restrict__ u, const int32_t* __restrict__ blocko
     }
 }
 
+// fo[m] = fftshift(Fs * fftfreq(L))[pos[m]] / foeM  (carrierRecovery.py:358-359, 368), same double arithmetic as numpy
+__global__ void k_foe_freq(const int64_t* __restrict__ pos, double* __restrict__ fo, int64_t L, int nModes, double Fs,
+                           int foeM) {
+    for (int m = threadIdx.x; m < nModes; m += blockDim.x) {
+        const int64_t j = pos[m];
+        int64_t k = j - L / 2;
+        if (k < 0) k += L;
+        const int64_t kk = (k <= (L - 1) / 2) ? k : k - L;
+        fo[m] = (Fs * ((double)kk / (double)L)) / (double)foeM;
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t ocb_cpr_workspace_bytes(int64_t L, int nModes) {
@@ -193,36 +206,23 @@ extern "C" int ocb_cpr_bps_run(const void* x_dev, int x_dtype, int64_t L, int nM
     const int gp = g > 4096 ? 4096 : g;
 
     if (runFOE) {
-        std::vector<double> fo(nModes, 0.0);
-        OCB_LAUNCH(k_foe_power, g, 256, 0, st, X, Z, L, nModes, foeM);
-        cufftHandle plan;
-        int len[1] = {(int)L};
         OCB_REQUIRE(L < (1ll << 31), "cpr_bps_run: L too large for the FOE transform");
-        OCB_CUFFT(cufftPlanMany(&plan, 1, len, nullptr, 1, (int)L, nullptr, 1, (int)L, CUFFT_Z2Z, nModes));
-        cufftResult r = cufftSetStream(plan, st);
-        if (r == CUFFT_SUCCESS) r = cufftExecZ2Z(plan, (cufftDoubleComplex*)Z, (cufftDoubleComplex*)Z, CUFFT_FORWARD);
-        if (r != CUFFT_SUCCESS) { cufftDestroy(plan); return fail("cpr_bps_run: FOE transform failed", __FILE__, __LINE__); }
+        OCB_LAUNCH(k_foe_power, g, 256, 0, st, X, Z, L, nModes, foeM);
+        cufftHandle plan;  // cached per (device, L, nModes): plan_cache.cuh
+        OCB_CUFFT(fft_plan_cached(CUFFT_Z2Z, (int)L, nModes, st, &plan));
+        OCB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)Z, (cufftDoubleComplex*)Z, CUFFT_FORWARD));
         k_foe_argmax<<<nModes, 1024, 0, st>>>(Z, L, pos);
         launch_counter()++;
-        std::vector<int64_t> hp(nModes);
-        cudaError_t e = cudaMemcpyAsync(hp.data(), pos, nModes * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        cufftDestroy(plan);
-        if (e != cudaSuccess) return fail(cudaGetErrorString(e), __FILE__, __LINE__);
-        for (int m = 0; m < nModes; ++m) {
-            // f = fftshift(Fs * fftfreq(L)); fo = f[indFO] / M   (:358-359, :368)
-            const int64_t j = hp[m];
-            int64_t k = j - L / 2;
-            if (k < 0) k += L;
-            const int64_t kk = (k <= (L - 1) / 2) ? k : k - L;
-            fo[m] = (Fs * ((double)kk / (double)L)) / (double)foeM;
-            if (fo_host) fo_host[m] = fo[m];
-        }
-        OCB_CUDA(cudaMemcpyAsync(fo_dev, fo.data(), nModes * sizeof(double), cudaMemcpyHostToDevice, st));
+        // f = fftshift(Fs * fftfreq(L)); fo = f[indFO] / M   (:358-359, :368) — evaluated on the device, the host
+        // copy of fo is fetched only when the caller asked for it
+        OCB_LAUNCH(k_foe_freq, 1, 32, 0, st, pos, fo_dev, L, nModes, Fs, foeM);
         OCB_LAUNCH(k_foe_apply, g, 256, 0, st, X, L, nModes, fo_dev, Fs);
-        OCB_CUDA(cudaStreamSynchronize(st));  // fo (host vector) is consumed
         OCB_LAUNCH(k_power_partials, gp, 256, 0, st, X, n, partials);  // pnorm (:130)
         OCB_LAUNCH(k_pnorm_scale, g, 256, 0, st, X, n, partials, gp);
+        if (fo_host) {
+            OCB_CUDA(cudaMemcpyAsync(fo_host, fo_dev, nModes * sizeof(double), cudaMemcpyDeviceToHost, st));
+            OCB_CUDA(cudaStreamSynchronize(st));
+        }
     } else if (fo_host) {
         for (int m = 0; m < nModes; ++m) fo_host[m] = 0.0;
     }

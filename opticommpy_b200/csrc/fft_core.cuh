@@ -66,6 +66,37 @@ __host__ __device__ constexpr int brev(int k) {
     return r;
 }
 
+// Packed FP32 pairs (sm_100a FADD2): a complex add / subtract is ONE instruction on the (re, im) register pair instead
+// of two.  The butterflies of the radix-2 stages are 60 % of a transform's additions.  Same IEEE results as two FADDs.
+// PK selects it per kernel: it pays in the time pass (instruction-fetch bound: 15 % fewer instructions, -6..-13 % time)
+// and costs 4 % in the frequency pass (math-pipe bound: FADD2 occupies the FMA pipe like two FADDs, while scalar FADDs
+// also issue to the second pipe) — measured on the B200, profiles/r2_summary.md.
+#ifndef OCB_F32X2
+#define OCB_F32X2 1
+#endif
+template <bool PK = true>
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    if constexpr (!PK) return make_float2(a.x + b.x, a.y + b.y);
+#if OCB_F32X2
+    unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b), ud;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    return *reinterpret_cast<float2*>(&ud);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+template <bool PK = true>
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    if constexpr (!PK) return make_float2(a.x - b.x, a.y - b.y);
+#if OCB_F32X2
+    unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b), ud;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    return *reinterpret_cast<float2*>(&ud);
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+
 // a * (h + l) and a * conj(h + l) for a double-single factor (l is ignored when OCB_DS = 0)
 __device__ __forceinline__ float2 cmul_ds(float2 a, float2 h, float2 l) {
     if constexpr (kDS) {
@@ -116,7 +147,7 @@ __device__ __forceinline__ float2 twiddle_mul(float2 t) {
 }
 
 // decimation in frequency: v natural -> X[k] at v[brev<R>(k)]
-template <int R, int DIR>
+template <int R, int DIR, bool PK = true>
 __device__ __forceinline__ void fft_dif(float2* v) {
     static_for<0, ilog2(R)>([&](auto st) {
         constexpr int LEN = R >> decltype(st)::value, HALF = LEN / 2;
@@ -125,15 +156,15 @@ __device__ __forceinline__ void fft_dif(float2* v) {
             static_for<0, HALF>([&](auto jj) {
                 constexpr int J = decltype(jj)::value;
                 const float2 a = v[BASE + J], b = v[BASE + J + HALF];
-                v[BASE + J] = make_float2(a.x + b.x, a.y + b.y);
-                v[BASE + J + HALF] = twiddle_mul<LEN, J, DIR>(make_float2(a.x - b.x, a.y - b.y));
+                v[BASE + J] = cadd<PK>(a, b);
+                v[BASE + J + HALF] = twiddle_mul<LEN, J, DIR>(csub<PK>(a, b));
             });
         });
     });
 }
 
 // decimation in time: v[brev<R>(n)] = x[n] on input -> X[k] at v[k]
-template <int R, int DIR>
+template <int R, int DIR, bool PK = true>
 __device__ __forceinline__ void fft_dit(float2* v) {
     static_for<0, ilog2(R)>([&](auto st) {
         constexpr int LEN = 2 << decltype(st)::value, HALF = LEN / 2;
@@ -143,8 +174,8 @@ __device__ __forceinline__ void fft_dit(float2* v) {
                 constexpr int J = decltype(jj)::value;
                 const float2 a = v[BASE + J];
                 const float2 b = twiddle_mul<LEN, J, DIR>(v[BASE + J + HALF]);
-                v[BASE + J] = make_float2(a.x + b.x, a.y + b.y);
-                v[BASE + J + HALF] = make_float2(a.x - b.x, a.y - b.y);
+                v[BASE + J] = cadd<PK>(a, b);
+                v[BASE + J + HALF] = csub<PK>(a, b);
             });
         });
     });
@@ -173,11 +204,11 @@ struct Coop {
 // HALF = true: the exchange runs in two rounds (real parts, then imaginary parts) through ONE planar array
 // (xr; xi unused), which halves the shared-memory footprint at the price of two more barriers per transform.
 // tw_lo: the lo parts of the table, same layout (read only when OCB_DS = 1)
-template <int Q, int CP, int PAD, bool HALF = false, typename SyncF>
+template <int Q, int CP, int PAD, bool HALF = false, bool PK = true, typename SyncF>
 __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi, const float2* __restrict__ tw,
                                                  const float2* __restrict__ tw_lo, int q, int c, SyncF&& sync) {
     constexpr int G = 32 / Q, STR = Q * CP + PAD;
-    fft_dif<32, -1>(v);  // v[brev5(ka)] = Z[ka]
+    fft_dif<32, -1, PK>(v);  // v[brev5(ka)] = Z[ka]
     if constexpr (!HALF) {
         static_for<0, 32>([&](auto kk) {
             constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
@@ -224,16 +255,16 @@ __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi
             });
         });
     }
-    static_for<0, G>([&](auto gg) { fft_dif<Q, -1>(v + decltype(gg)::value * Q); });
+    static_for<0, G>([&](auto gg) { fft_dif<Q, -1, PK>(v + decltype(gg)::value * Q); });
 }
 
 // twt / twt_lo: the TRANSPOSED copy of the table (hi and lo parts), entry [J][ka]; for Q = 32 the table is
 // symmetric and the transposed copy is the table itself.
-template <int Q, int CP, int PAD, bool HALF = false, typename SyncF>
+template <int Q, int CP, int PAD, bool HALF = false, bool PK = true, typename SyncF>
 __device__ __forceinline__ void coop_fft_inverse(float2* v, float* xr, float* xi, const float2* __restrict__ twt,
                                                  const float2* __restrict__ twt_lo, int q, int c, SyncF&& sync) {
     constexpr int G = 32 / Q, STR = Q * CP + PAD;
-    static_for<0, G>([&](auto gg) { fft_dit<Q, +1>(v + decltype(gg)::value * Q); });  // over kq -> q'
+    static_for<0, G>([&](auto gg) { fft_dit<Q, +1, PK>(v + decltype(gg)::value * Q); });  // over kq -> q'
     static_for<0, G>([&](auto gg) {
         constexpr int GI = decltype(gg)::value;
         const int ka = q * G + GI;
@@ -267,7 +298,7 @@ __device__ __forceinline__ void coop_fft_inverse(float2* v, float* xr, float* xi
             v[SLOT] = make_float2(re[KA], xr[KA * STR + q * CP + c]);
         });
     }
-    fft_dit<32, +1>(v);  // natural a'
+    fft_dit<32, +1, PK>(v);  // natural a'
 }
 
 }  // namespace fft

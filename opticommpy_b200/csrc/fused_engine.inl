@@ -13,7 +13,7 @@ bool pdl_enabled() {
 
 // One-time per-DEVICE setup (function attributes and device limits are per device/context, and one process may
 // drive several GPUs): true the first time `slot` is seen on the current device.
-enum OnceSlot { ONCE_L2_LIMIT = 0, ONCE_FREQ_BASE = 1, ONCE_SLOTS = 16 };
+enum OnceSlot { ONCE_L2_LIMIT = 0, ONCE_FREQ_BASE = 1, ONCE_TIME_BASE = 16, ONCE_SLOTS = 32 };
 bool first_time_on_device(int slot) {
     static bool done[ONCE_SLOTS][64] = {};
     int dev = 0;
@@ -31,7 +31,24 @@ int launch_time_t(const TimeArgs& a, cudaStream_t st) {
     return 0;
 }
 template <int NP, int MODE>
+int launch_time_bulk(const TimeArgs& a, cudaStream_t st) {
+    if (first_time_on_device(ONCE_TIME_BASE + (NP - 1) * 7 + MODE))
+        OCB_CUDA(cudaFuncSetAttribute(k_time_bulk<NP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TimeBulkCfg::SMEM_BYTES));
+    const int grid = a.N2 < kNumSMs ? a.N2 : kNumSMs;
+    OCB_LAUNCH_PDL((k_time_bulk<NP, MODE>), grid, 256, TimeBulkCfg::SMEM_BYTES, st, pdl_enabled(), a);
+    return 0;
+}
+// Time-pass kernel per mode (measured on the B200, profiles/r2_summary.md): the fixed-point iteration passes TM_ITER /
+// TM_ITERF at N1 = 1024 run on the persistent bulk-copy-fed kernel (fused_time_bulk.cuh: E_c, E_hd and P_ch arrive by
+// cp.async.bulk issued before the dependency wait), every other pass on the one-wave kernel.  OCB_TIME_KERNEL=plain /
+// bulk (read when a plan is created) forces one of them for every mode (A/B knob); all choices produce bit-identical
+// fields.  The knobs live in the plan: see read_engine_knobs().
+template <int NP, int MODE>
 int launch_time(int Q1, const TimeArgs& a, cudaStream_t st) {
+    const int choice = a.kernel_choice;
+    if (Q1 == 32 && (choice == 1 || (choice == 0 && (MODE == TM_ITER || MODE == TM_ITERF))))
+        return launch_time_bulk<NP, MODE>(a, st);
     switch (Q1) {
         case 8: return launch_time_t<8, NP, MODE>(a, st);
         case 16: return launch_time_t<16, NP, MODE>(a, st);
@@ -39,11 +56,12 @@ int launch_time(int Q1, const TimeArgs& a, cudaStream_t st) {
     }
     return fail("fused engine: unsupported N1", __FILE__, __LINE__);
 }
-// W positions per k_freq tile of the main kernels when N2 = 1024: 16 (128-byte row segments, one 512-thread CTA
-// per SM; default) or 8 (64-byte segments, two 256-thread CTAs per SM); OCB_FREQ_C is a tuning knob read once
-int freq_c() {
-    static const int c = (getenv("OCB_FREQ_C") && atoi(getenv("OCB_FREQ_C")) == 8) ? 8 : 16;  // 16 measured 7 % faster per pass
-    return c;
+// W positions per k_freq tile when N2 = 1024: 4 for the TMA-fed kernel (fused_freq_tma.cuh, default), else 16 (128-byte
+// row segments, one 512-thread CTA per SM) or 8; OCB_FREQ_TMA=0 / OCB_FREQ_C are A/B knobs read when a plan is created.
+// All variants produce bit-identical fields (same arithmetic, different data path).
+int freq_c(const ocb_ssfm_plan* p) {
+    if (p->q2 != 32) return kFreqC;
+    return (p->knob_freq_tma && p->wmap_ok) ? FreqTmaCfg::C : p->knob_freq_c;
 }
 template <int Q2, int C>
 int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP, const long long* flag,
@@ -54,10 +72,31 @@ int launch_freq_t(float2* W, const float2* LP, const float2* tw, int N1, int NP,
     OCB_LAUNCH_PDL((k_freq<Q2, C>), NP * N1 / C, Q2 * C, smem, st, pdl_enabled(), W, LP, tw, N1, flag, step_id, need_flag, need_id);
     return 0;
 }
-int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, int NP, cudaStream_t st,
+int launch_freq(ocb_ssfm_plan* p, const float2* LP, int NP, cudaStream_t st,
                 const long long* flag = nullptr, long long step_id = 0, const long long* need_flag = nullptr,
                 long long need_id = 0) {
-    if (freq_c() == 16 && Q2 == 32) return launch_freq_t<32, 16>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
+    float2* W = p->G;
+    const float2* tw = p->tw2;
+    const int N1 = 32 * p->q1, Q2 = p->q2;
+    const int c = freq_c(p);
+    if (Q2 == 32 && c == FreqTmaCfg::C) {
+        const bool lockstep = p->knob_freq_lockstep;
+        if (first_time_on_device(ONCE_FREQ_BASE + 14)) {
+            OCB_CUDA(cudaFuncSetAttribute(k_freq_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FreqTmaCfg::SMEM_BYTES));
+            OCB_CUDA(cudaFuncSetAttribute(k_freq_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FreqTmaCfg::SMEM_BYTES));
+        }
+        const int tiles = NP * N1 / FreqTmaCfg::C;
+        const int grid = tiles / FreqTmaCfg::GROUPS;  // 128 CTAs (dual-pol): every group of every CTA owns one tile
+        OCB_REQUIRE(grid * FreqTmaCfg::GROUPS == tiles && grid <= kNumSMs, "k_freq_tma: unexpected tile count");
+        if (lockstep)
+            OCB_LAUNCH_PDL(k_freq_tma<true>, grid, 512, FreqTmaCfg::SMEM_BYTES, st, pdl_enabled(), p->wmap, LP, tw, N1, NP,
+                           flag, step_id, need_flag, need_id);
+        else
+            OCB_LAUNCH_PDL(k_freq_tma<false>, grid, 512, FreqTmaCfg::SMEM_BYTES, st, pdl_enabled(), p->wmap, LP, tw, N1, NP,
+                           flag, step_id, need_flag, need_id);
+        return 0;
+    }
+    if (c == 16 && Q2 == 32) return launch_freq_t<32, 16>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
     switch (Q2) {
         case 8: return launch_freq_t<8, kFreqC>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
         case 16: return launch_freq_t<16, kFreqC>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);
@@ -68,7 +107,7 @@ int launch_freq(int Q2, float2* W, const float2* LP, const float2* tw, int N1, i
 int launch_linop_perm(ocb_ssfm_plan* p, float2* LP, double a, double b, double Fs, double h, double scale,
                       cudaStream_t st) {
     OCB_LAUNCH(k_tab_linop_perm, grid_for(p->N, 256, 1), 256, 0, st, LP, p->q1, p->q2,
-               (p->q2 == 32 ? freq_c() : kFreqC), p->N, a, b, Fs, h, scale);
+               freq_c(p), p->N, a, b, Fs, h, scale);
     return 0;
 }
 // natural planar rows [r][N2*n1 + n2] -> engine layout [r][N1*n2 + n1] (to_engine) or back
@@ -97,6 +136,7 @@ TimeArgs time_base(ocb_ssfm_plan* p) {
     a.tw = p->tw1; a.tabV = p->tabV; a.tabU = p->tabU;
     a.partials = p->partials; a.sums = p->sums; a.ticket = p->ticket;
     a.N = p->N; a.N2 = 32 * p->q2; a.out_scale = 1.0f; a.cphi = 0.f;
+    a.kernel_choice = p->knob_time_kernel;
     return a;
 }
 
@@ -209,7 +249,7 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                                     long long need_id) -> int {
                 {
                     ProfScope ps(p, 2, st);
-                    if (launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, p->conv_flag, sid, need, need_id)) return 1;
+                    if (launch_freq(p, LP, R, st, p->conv_flag, sid, need, need_id)) return 1;
                 }
                 ProfScope ps(p, 0, st);
                 const TimeArgs ci = time_args_iter(sid, seq, final_pred, need, need_id);
@@ -225,7 +265,7 @@ static int fused_manakov_run(ocb_ssfm_plan* p, void* rows_inout, const ocb_manak
                         c0.in = p->A; c0.out = Wb;
                         if (launch_time<2, TM_FWD>(p->q1, c0, st)) return 1;
                     }
-                    if (launch_freq(p->q2, Wb, LP, p->tw2, N1, R, st, nullptr, 0, need, need_id)) return 1;
+                    if (launch_freq(p, LP, R, st, nullptr, 0, need, need_id)) return 1;
                 }
                 ProfScope ps(p, 1, st);
                 TimeArgs c1 = time_base(p);
@@ -346,12 +386,12 @@ static int fused_nlse_run(ocb_ssfm_plan* p, void* row_inout, const ocb_nlse_para
             cf.in = E; cf.out = Wb;
             if (launch_time<1, TM_FWD>(p->q1, cf, st)) return 1;  // channels.py:216 (time half)
             for (int s = 0; s < q->n_steps; ++s) {
-                if (launch_freq(p->q2, Wb, s == 0 ? p->T1 : p->T2, p->tw2, N1, 1, st)) return 1;
+                if (launch_freq(p, s == 0 ? p->T1 : p->T2, 1, st)) return 1;
                 TimeArgs cn = time_base(p);
                 cn.in = Wb; cn.out = Wb; cn.cphi = (float)(q->gamma * q->hz);
                 if (launch_time<1, TM_NLSE>(p->q1, cn, st)) return 1;  // :224-228
             }
-            if (launch_freq(p->q2, Wb, p->T1, p->tw2, N1, 1, st)) return 1;  // :229 of the last step
+            if (launch_freq(p, p->T1, 1, st)) return 1;  // :229 of the last step
             TimeArgs ci = time_base(p);
             ci.in = Wb; ci.out = E; ci.out_scale = gain;
             if (launch_time<1, TM_INV>(p->q1, ci, st)) return 1;  // :232 + gain of :234/:236
@@ -382,7 +422,7 @@ extern "C" int ocb_ssfm_plan_pass_time(ocb_ssfm_plan* p, int which, int reps, do
         TimeArgs a = time_base(p);
         a.in = p->G; a.out = p->G; a.aux0 = p->A; a.aux1 = p->A; a.ehd = p->Ehd; a.pch = p->Pch; a.cphi = 1e-3f;
         switch (which) {
-            case 0: return launch_freq(p->q2, p->G, p->T1, p->tw2, N1, 2, st);
+            case 0: return launch_freq(p, p->T1, 2, st);
             case 1: a.aux1 = p->Ehd; return launch_time<2, TM_FIRST>(p->q1, a, st);
             case 2: return launch_time<2, TM_ITER>(p->q1, a, st);
             case 3: return launch_time<2, TM_ITERF>(p->q1, a, st);

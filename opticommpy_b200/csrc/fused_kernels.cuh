@@ -53,6 +53,7 @@ struct TimeArgs {
     FinalizeExt ext;      // TM_ITER: host mailbox + convergence flag (ext.mail == nullptr: unused)
     const long long* need_flag;  // speculative launch across a step boundary: run only if *need_flag == need_id
     long long need_id;
+    int kernel_choice;    // host side only: 0 per-mode default, 1 bulk-copy-fed kernel, 2 one-wave kernel (launch_time)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -327,11 +328,11 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
     for (int a = 0; a < 32; ++a) v[a] = ld_stream(base + (int64_t)(Q2 * a + q) * N1);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // twiddle table and operator slice staged
-    coop_fft_forward<Q2, C, C, true>(v, xr, nullptr, tws, tws_lo, q, c, bsync);
+    coop_fft_forward<Q2, C, C, true, false>(v, xr, nullptr, tws, tws_lo, q, c, bsync);
 #pragma unroll
     for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], lps[s * NT + tid]);
     __syncthreads();
-    coop_fft_inverse<Q2, C, C, true>(v, xr, nullptr, twt, twt_lo, q, c, bsync);
+    coop_fft_inverse<Q2, C, C, true, false>(v, xr, nullptr, twt, twt_lo, q, c, bsync);
 #pragma unroll
     for (int a = 0; a < 32; ++a) st_stream(base + (int64_t)(Q2 * a + q) * N1, v[a]);
 }

@@ -10,6 +10,7 @@
 
 #include "../../include/opticomm_b200.h"
 #include "common.cuh"
+#include "plan_cache.cuh"
 
 using namespace ocb;
 
@@ -100,33 +101,19 @@ extern "C" int ocb_edc_run(const void* x_rows, void* y_rows, int64_t L, int nMod
     const int64_t nseg = (int64_t)nModes * g.nblk;
     OCB_REQUIRE(nseg < (1ll << 31), "edc_run: too many blocks");
 
+    // plans come from the per-process cache (plan_cache.cuh): no allocation, no host synchronisation in this call
     cufftHandle ph, pb;
-    OCB_CUFFT(cufftPlan1d(&ph, g.nfft, CUFFT_C2C, 1));
-    int n[1] = {g.nfft};
-    cufftResult r = cufftPlanMany(&pb, 1, n, nullptr, 1, g.nfft, nullptr, 1, g.nfft, CUFFT_C2C, (int)nseg);
-    if (r != CUFFT_SUCCESS) { cufftDestroy(ph); return fail("edc_run: cufftPlanMany failed", __FILE__, __LINE__); }
-    int rc = 0;
-    do {
-        if (cufftSetStream(ph, st) != CUFFT_SUCCESS || cufftSetStream(pb, st) != CUFFT_SUCCESS) { rc = fail("edc_run: cufftSetStream", __FILE__, __LINE__); break; }
-        k_edc_pad_taps<<<grid_for(g.nfft, 256, 1), 256, 0, st>>>((const float2*)h_taps, Hf, K, g.nfft);
-        launch_counter()++;
-        if (cufftExecC2C(ph, Hf, Hf, CUFFT_FORWARD) != CUFFT_SUCCESS) { rc = fail("edc_run: fft(h)", __FILE__, __LINE__); break; }  // core.py:1020
-        k_edc_gather<<<grid_for(nseg * g.nfft, 256, 4), 256, 0, st>>>((const float2*)x_rows, seg, L, g.nfft, g.d, g.nblk, D - (K - 1), nModes);
-        launch_counter()++;
-        if (cufftExecC2C(pb, seg, seg, CUFFT_FORWARD) != CUFFT_SUCCESS) { rc = fail("edc_run: fft(blocks)", __FILE__, __LINE__); break; }
-        k_edc_mul<<<grid_for(nseg * g.nfft, 256, 4), 256, 0, st>>>(seg, Hf, nseg * g.nfft, g.nfft, 1.0f / (float)g.nfft);
-        launch_counter()++;
-        if (cufftExecC2C(pb, seg, seg, CUFFT_INVERSE) != CUFFT_SUCCESS) { rc = fail("edc_run: ifft(blocks)", __FILE__, __LINE__); break; }
-        k_edc_scatter<<<grid_for(nseg * g.d, 256, 4), 256, 0, st>>>(seg, (float2*)y_rows, L, g.nfft, g.d, g.nblk, K, nModes);
-        launch_counter()++;
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { rc = fail(cudaGetErrorString(e), __FILE__, __LINE__); break; }
-        e = cudaStreamSynchronize(st);  // plans are destroyed below
-        if (e != cudaSuccess) { rc = fail(cudaGetErrorString(e), __FILE__, __LINE__); break; }
-    } while (0);
-    cufftDestroy(ph);
-    cufftDestroy(pb);
-    return rc;
+    OCB_CUFFT(fft_plan_cached(CUFFT_C2C, g.nfft, 1, st, &ph));
+    OCB_CUFFT(fft_plan_cached(CUFFT_C2C, g.nfft, (int)nseg, st, &pb));
+    OCB_LAUNCH(k_edc_pad_taps, grid_for(g.nfft, 256, 1), 256, 0, st, (const float2*)h_taps, Hf, K, g.nfft);
+    OCB_CUFFT(cufftExecC2C(ph, Hf, Hf, CUFFT_FORWARD));  // core.py:1020
+    OCB_LAUNCH(k_edc_gather, grid_for(nseg * g.nfft, 256, 4), 256, 0, st, (const float2*)x_rows, seg, L, g.nfft, g.d, g.nblk,
+               D - (K - 1), nModes);
+    OCB_CUFFT(cufftExecC2C(pb, seg, seg, CUFFT_FORWARD));
+    OCB_LAUNCH(k_edc_mul, grid_for(nseg * g.nfft, 256, 4), 256, 0, st, seg, Hf, nseg * g.nfft, g.nfft, 1.0f / (float)g.nfft);
+    OCB_CUFFT(cufftExecC2C(pb, seg, seg, CUFFT_INVERSE));
+    OCB_LAUNCH(k_edc_scatter, grid_for(nseg * g.d, 256, 4), 256, 0, st, seg, (float2*)y_rows, L, g.nfft, g.d, g.nblk, K, nModes);
+    return 0;
 }
 
 // =============================================================================================

@@ -13,6 +13,8 @@
 #include "../../include/opticomm_b200.h"
 #include "ssfm_kernels.cuh"
 #include "fused_kernels.cuh"
+#include "fused_time_bulk.cuh"
+#include "fused_freq_tma.cuh"
 
 using namespace ocb;
 
@@ -67,6 +69,13 @@ struct ocb_ssfm_plan {
     int q1 = 0, q2 = 0;
     float2 *tw1 = nullptr, *tw2 = nullptr, *tabV = nullptr, *tabU = nullptr;
     float2 *Cb = nullptr, *Nb = nullptr;  // third rotating field buffer, engine-layout noise copy
+    // tuning / A-B knobs, read from the environment when the plan is created (fused_engine.inl)
+    int knob_time_kernel = 0;       // OCB_TIME_KERNEL: 0 per-mode default, 1 "bulk", 2 "plain"
+    bool knob_freq_tma = true;      // OCB_FREQ_TMA=0: classic k_freq instead of the TMA-fed one
+    bool knob_freq_lockstep = false;  // OCB_FREQ_LOCKSTEP=1: CTA-wide instead of per-group barriers in k_freq_tma
+    int knob_freq_c = 16;           // OCB_FREQ_C=8: tile width of the classic k_freq at N2 = 1024
+    CUtensorMap wmap;      // W buffer as float32 [rows][N2][2*N1] for the TMA-fed frequency pass (N2 = 1024)
+    bool wmap_ok = false;
     // table cache keys
     double t1_h = NAN, t1_a = NAN, t1_b = NAN, t1_scale = NAN;
     // optional in-situ kernel timing (CUDA events on the launching stream); kinds:
@@ -114,6 +123,37 @@ static int fused_manakov_run(ocb_ssfm_plan*, void*, const ocb_manakov_params*, c
 static int fused_nlse_run(ocb_ssfm_plan*, void*, const ocb_nlse_params*, const void*, cudaStream_t);
 static bool use_fused(const ocb_ssfm_plan* p) { return p->fused_ok && p->engine != OCB_ENGINE_CUFFT; }
 
+// Tensor map of the W buffer for k_freq_tma: float32 elements, dims (fastest first) {2*N1, N2, rows}, box
+// {2*C, 256, 1} = one 32-byte row segment x 256 rows.  cuTensorMapEncodeTiled is fetched through the runtime
+// (cudaGetDriverEntryPoint), so the library does not link libcuda.  A driver without it leaves wmap_ok = false and the
+// classic k_freq runs.
+static int make_w_tensor_map(ocb_ssfm_plan* p) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    const cuuint64_t N1 = 32ull * p->q1, N2 = 32ull * p->q2;
+    cuuint64_t dims[3] = {2 * N1, N2, (cuuint64_t)p->rows};
+    cuuint64_t strides[2] = {N1 * 8, N1 * N2 * 8};  // bytes, dims 1 and 2
+    cuuint32_t box[3] = {2 * FreqTmaCfg::C, FreqTmaCfg::BOX_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeFn)fn)(&p->wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->G, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[128]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return fail(b, __FILE__, __LINE__);
+    }
+    p->wmap_ok = true;
+    return 0;
+}
+
 extern "C" int ocb_abi_version(void) { return OCB_ABI_VERSION; }
 extern "C" const char* ocb_last_error(void) { return last_error().c_str(); }
 extern "C" int64_t ocb_launch_count(void) { return launch_counter(); }
@@ -127,6 +167,13 @@ extern "C" int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out) {
     p->N = N;
     p->rows = rows;
     p->fused_ok = (rows == 1 || rows == 2) && fused_geometry(N, &p->q1, &p->q2);
+    {
+        const char* v = getenv("OCB_TIME_KERNEL");
+        p->knob_time_kernel = (v && !strcmp(v, "bulk")) ? 1 : (v && !strcmp(v, "plain")) ? 2 : 0;
+        p->knob_freq_tma = !(getenv("OCB_FREQ_TMA") && atoi(getenv("OCB_FREQ_TMA")) == 0);
+        p->knob_freq_lockstep = getenv("OCB_FREQ_LOCKSTEP") && atoi(getenv("OCB_FREQ_LOCKSTEP")) != 0;
+        p->knob_freq_c = (getenv("OCB_FREQ_C") && atoi(getenv("OCB_FREQ_C")) == 8) ? 8 : 16;
+    }
     if (cufftCreate(&p->fft) != CUFFT_SUCCESS) { delete p; return fail("cufftCreate failed", __FILE__, __LINE__); }
     p->fft_ok = true;
     if (cufftSetAutoAllocation(p->fft, 0) != CUFFT_SUCCESS) { ocb_ssfm_plan_destroy(p); return fail("cufftSetAutoAllocation failed", __FILE__, __LINE__); }
@@ -189,6 +236,8 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
         p->Cb = (float2*)c; c += align_up((int64_t)p->rows * p->N * 8, 256);
         p->Nb = (float2*)c; c += align_up(p->N * 8, 256);
         p->fused_tables_ready = false;
+        p->wmap_ok = false;
+        if (p->q2 == 32 && make_w_tensor_map(p)) return 1;
     }
     OCB_CUDA(cudaMemset(p->sums, 0, 256));
     p->t1_h = NAN;
