@@ -280,6 +280,38 @@ int64_t ocb_decimate_workspace_bytes(int nModes, int SpSin);
 int ocb_decimate_run(const void* x_rows, void* y_rows, int64_t N, int nModes, int SpSin, int decFactor,
                      void* delays_dev, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Polarisation-multiplexed coherent front end with ideal photodiodes, one pass over the samples.
+ * Replaces: optic.models.devices.pdmCoherentReceiver (optic/models/devices.py:574-668) with paramPD.ideal = True and
+ * without polarisation delay / IQ skew (the host mirror composes those from the FIR path): pbs rotation of the signal
+ * (:223-262), PDL, 45-degree LO split, opticalHybrid2x4 (:447-503), balancedPD (:402-444) with photodiode R |E|^2
+ * (:313-318), iqMixing amplitude / phase imbalance (optic/dsp/core.py:951-959; iq_k = k1x, k2x, k1y, k2y as (re, im)).
+ *   Es_rows : planar [2][N] complex64 (x, y) ; S_rows : [2][N] complex64 out
+ *   Elo     : [N] complex64 LO field, or NULL for a noiseless CW LO sqrt(lo_power_w) exp(j 2 pi lo_freq_shift n / Fs)
+ *             generated on the fly — the channel down-shift of a WDM receiver (basicLaserModel with lw = 0, RIN = 0,
+ *             devices.py:729-791).                                                                                  */
+int ocb_pdm_frontend_run(const void* Es_rows, const void* Elo, void* S_rows, int64_t N, double polRotation,
+                         double pdl_dB, double R, double lo_power_w, double lo_freq_shift, double Fs,
+                         const double* iq_k, void* stream);
+/* rows[r][n] *= exp(-j 2 pi freq n / Fs): stand-alone frequency down-shift of planar complex64 rows, in place. */
+int ocb_freq_shift_run(void* rows, int nRows, int64_t N, double freq, double Fs, void* stream);
+
+/* symbolSync building blocks (optic/dsp/core.py:552-675; finddelay :678-698).  The decisions (column swap, pi/2
+ * rotation, conjugation, delay) are scalars taken on the host from the correlation peaks; everything of length L runs
+ * on the device.
+ *   ocb_sync_sequence_run : column r of an (L, nCols) complex128 array -> real row out[r][L] (double):
+ *                           kind 0: |z| - mean|z| (:605-608), 1: Re z, 2: Im z (:628-629)
+ *   ocb_xcorr_peak_run    : for every pair (a_i, b_j) of real rows, the first index k maximising |c[k]| of
+ *                           c = scipy.signal.correlate(a_i, b_j, 'full') and the value c[k]; results in host arrays
+ *                           indexed i*nB + j.  Synchronises the stream.
+ *   ocb_sync_apply_run    : out[n][k] = conj?(rot[k] * tx[(n + delay[k]) mod L][swap[k]])  (:648-666), complex128   */
+int ocb_sync_sequence_run(const void* z_dev, int nCols, int64_t L, int kind, void* out_rows, void* stream);
+int64_t ocb_xcorr_workspace_bytes(int nA, int64_t La, int nB, int64_t Lb);
+int ocb_xcorr_peak_run(const void* a_rows, int nA, int64_t La, const void* b_rows, int nB, int64_t Lb,
+                       int64_t* peak_idx_host, double* peak_val_host, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+int ocb_sync_apply_run(const void* tx_dev, void* out_dev, int64_t L, int nCols, const int32_t* swap_dev,
+                       const void* rot_dev, const int32_t* conj_dev, const int64_t* delay_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

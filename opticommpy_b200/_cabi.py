@@ -93,6 +93,12 @@ SIGNATURES = {
     "ocb_cpr_workspace_bytes": (_i64, [_i64, _i]),
     "ocb_cpr_bps_run": (_i, [_vp, _i, _i64, _i, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp, C.POINTER(C.c_double), _vp,
                              _i64, _vp]),
+    "ocb_pdm_frontend_run": (_i, [_vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _d, C.POINTER(C.c_double), _vp]),
+    "ocb_freq_shift_run": (_i, [_vp, _i, _i64, _d, _d, _vp]),
+    "ocb_sync_sequence_run": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "ocb_xcorr_workspace_bytes": (_i64, [_i, _i64, _i, _i64]),
+    "ocb_xcorr_peak_run": (_i, [_vp, _i, _i64, _vp, _i, _i64, C.POINTER(C.c_int64), C.POINTER(C.c_double), _vp, _i64, _vp]),
+    "ocb_sync_apply_run": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "ocb_min_euclid": (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp, _vp]),
     "ocb_ber_workspace_bytes": (_i64, [_i]),
     "ocb_ber_count": (_i, [_vp, _vp, _i, _i64, _i, _vp, _i, _i, _d, C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -65,6 +65,30 @@ def bps(sigIn, N, constSymb, B, returnIndex=False):
     return phaseEst
 
 
+def cpr_bps_device(d_x, x_dtype_tag, L, nModes, constSymb, B, N, runFOE, Fs, foeM, want_fo=False):
+    """Device-resident cpr(alg='bps'): ``d_x`` holds (L, nModes) interleaved complex samples on the GPU (complex64 or
+    complex128 as float pairs, ``x_dtype_tag``).  Returns (d_y (L, nModes, 2) float64, d_phase (L, nModes) float64,
+    fo ctypes array or None, temporaries to keep alive).  Synchronises only when the frequency offsets are requested."""
+    torch = _cabi.require_cuda()
+    lib = _cabi.lib()
+    st = _vp(_cabi.stream_ptr(torch))
+    c128 = np.ascontiguousarray(np.asarray(constSymb).astype(np.complex128))
+    d_c = torch.from_numpy(c128.view(np.float64)).to("cuda")
+    d_y = torch.empty((L, nModes, 2), dtype=torch.float64, device="cuda")
+    d_ph = torch.empty((L, nModes), dtype=torch.float64, device="cuda")
+    ws_bytes = int(lib.ocb_cpr_workspace_bytes(L, nModes))
+    d_ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (d_ws.data_ptr() + 255) // 256 * 256
+    fo = (C.c_double * nModes)() if want_fo else None
+    _cabi.check(
+        lib.ocb_cpr_bps_run(_vp(d_x.data_ptr()), x_dtype_tag, L, nModes, _vp(d_c.data_ptr()), len(c128),
+                            int(B), int(N // 2), int(bool(runFOE)), float(Fs), int(foeM), _vp(d_y.data_ptr()),
+                            _vp(d_ph.data_ptr()), fo, _vp(ws_ptr), ws_bytes, st),
+        "ocb_cpr_bps_run",
+    )
+    return d_y, d_ph, fo, (d_c, d_ws)
+
+
 def cpr(sigIn, param=None, symbTx=None):
     """
     Carrier phase recovery (CPR) with the BPS algorithm on the GPU.
@@ -106,31 +130,18 @@ def cpr(sigIn, param=None, symbTx=None):
 
     # FOE + pnorm (:124-131), bps (:138), unwrap(4φ)/4 (:154) and pnorm(x·e^{jφ}) (:162) in one device call
     torch = _cabi.require_cuda()
-    lib = _cabi.lib()
     from . import _engine
     x = _engine.as_host_complex(sigIn)
     L, nModes = x.shape
-    c128 = np.ascontiguousarray(constSymb.astype(np.complex128))
-    st = _vp(_cabi.stream_ptr(torch))
     d_x = torch.from_numpy(x.view(np.float32 if x.dtype == np.complex64 else np.float64)).to("cuda")
-    d_c = torch.from_numpy(c128.view(np.float64)).to("cuda")
-    d_y = torch.empty((L, nModes, 2), dtype=torch.float64, device="cuda")
-    d_ph = torch.empty((L, nModes), dtype=torch.float64, device="cuda")
-    ws_bytes = int(lib.ocb_cpr_workspace_bytes(L, nModes))
-    d_ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
-    ws_ptr = (d_ws.data_ptr() + 255) // 256 * 256
-    fo = (C.c_double * nModes)()
     foeM = M if constType in ["psk", "apsk"] else 4
     if runFOE:
         logg.info("Running frequency offset compensation...")
     logg.info("Running BPS carrier phase recovery...")
-    _cabi.check(
-        lib.ocb_cpr_bps_run(_vp(d_x.data_ptr()), _engine.dtype_tag(x.dtype), L, nModes, _vp(d_c.data_ptr()), len(c128),
-                            int(B), int(N // 2), int(bool(runFOE)), float(1 / Ts), int(foeM), _vp(d_y.data_ptr()),
-                            _vp(d_ph.data_ptr()), fo, _vp(ws_ptr), ws_bytes, st),
-        "ocb_cpr_bps_run",
-    )
-    if runFOE:
+    want_fo = runFOE and logg.getLogger().isEnabledFor(logg.INFO)
+    d_y, d_ph, fo, _keep = cpr_bps_device(d_x, _engine.dtype_tag(x.dtype), L, nModes, constSymb, B, N, runFOE, 1 / Ts, foeM,
+                                          want_fo=want_fo)
+    if want_fo:
         logg.info(f"Estimated frequency offset (MHz): {np.round(np.array(fo[:]) / 1e6, 3)}")
     sigOut = d_y.cpu().numpy().view(np.complex128).reshape(L, nModes)
     phaseEst = d_ph.cpu().numpy()

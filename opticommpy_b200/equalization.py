@@ -30,6 +30,51 @@ def _to_device(torch, a: np.ndarray):
 
 
 # ------------------------------------------------------------------------------------------------
+def _edc_taps(param, Fs):
+    """Time-domain taps of the EDC filter exactly as the reference builds them (equalization.py:90-105 and
+    core.py:1016): returns (h complex64 of K taps, K, Nfft)."""
+    L = getattr(param, "L", 50)
+    D = getattr(param, "D", 16)
+    Fc = getattr(param, "Fc", 193.1e12)
+    Rs = getattr(param, "Rs", 32e9)
+    NfilterCoeffs = getattr(param, "NfilterCoeffs", None)
+    Nfft = getattr(param, "Nfft", None)
+
+    _, beta2 = _fiber_constants(0.0, D, Fc)
+    if NfilterCoeffs is None:  # equalization.py:96-97
+        NfilterCoeffs = int(2 * np.ceil(6.67 * np.abs(beta2) * L * Rs**2 * (Fs / Rs)))
+    if Nfft is None:  # equalization.py:100-101
+        Nfft = 2 ** int(np.ceil(np.log2(NfilterCoeffs)))
+    if Nfft < NfilterCoeffs:
+        logg.error("FFT size is smaller than filter length")
+        raise NameError("name 'd' is not defined")  # core.py:1009-1012 leaves d unbound
+    K = int(NfilterCoeffs)
+    if K < 1:
+        raise ValueError("EDC filter needs at least one coefficient")
+    w = 2 * np.pi * Fs * fftfreq(K)
+    H = np.exp(-1j * (beta2 / 2) * (w**2) * L)        # equalization.py:103-105
+    h = fftshift(ifft(H)).astype(np.complex64)        # core.py:1016 (time-domain taps, float64 math)
+    return h, K, Nfft
+
+
+def edc_rows_device(d_x, d_y, h):
+    """Device-resident EDC / FIR stage: planar rows ``d_x`` (nModes, N, 2) float32 CUDA -> ``d_y`` (same shape) through
+    ``ocb_edc_run`` with the complex64 taps ``h`` (host array).  No host synchronisation; returns the temporaries that
+    must stay alive until the stream has consumed them."""
+    torch = _cabi.require_cuda()
+    lib = _cabi.lib()
+    st = _vp(_cabi.stream_ptr(torch))
+    nModes, Nsig = int(d_x.shape[0]), int(d_x.shape[1])
+    K = len(h)
+    d_h = _to_device(torch, np.ascontiguousarray(h).view(np.float32))
+    ws_bytes = int(lib.ocb_edc_workspace_bytes(Nsig, nModes, K))
+    d_ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (d_ws.data_ptr() + 255) // 256 * 256
+    _cabi.check(lib.ocb_edc_run(_ptr(d_x), _ptr(d_y), Nsig, nModes, _ptr(d_h), K, _vp(ws_ptr), ws_bytes, st),
+                "ocb_edc_run")
+    return d_h, d_ws
+
+
 def edc(sigIn, param):
     """
     Electronic chromatic dispersion compensation (EDC) on the GPU.
@@ -50,28 +95,7 @@ def edc(sigIn, param):
         sigIn = sigIn.reshape(sigIn.size, nModes)
         input1D = True
 
-    L = getattr(param, "L", 50)
-    D = getattr(param, "D", 16)
-    Fc = getattr(param, "Fc", 193.1e12)
-    Rs = getattr(param, "Rs", 32e9)
-    NfilterCoeffs = getattr(param, "NfilterCoeffs", None)
-    Nfft = getattr(param, "Nfft", None)
-
-    _, beta2 = _fiber_constants(0.0, D, Fc)
-    if NfilterCoeffs is None:  # equalization.py:96-97
-        NfilterCoeffs = int(2 * np.ceil(6.67 * np.abs(beta2) * L * Rs**2 * (Fs / Rs)))
-    if Nfft is None:  # equalization.py:100-101
-        Nfft = 2 ** int(np.ceil(np.log2(NfilterCoeffs)))
-    if Nfft < NfilterCoeffs:
-        logg.error("FFT size is smaller than filter length")
-        raise NameError("name 'd' is not defined")  # core.py:1009-1012 leaves d unbound
-    K = int(NfilterCoeffs)
-    if K < 1:
-        raise ValueError("EDC filter needs at least one coefficient")
-
-    w = 2 * np.pi * Fs * fftfreq(K)
-    H = np.exp(-1j * (beta2 / 2) * (w**2) * L)        # equalization.py:103-105
-    h = fftshift(ifft(H)).astype(np.complex64)        # core.py:1016 (time-domain taps, float64 math)
+    h, K, Nfft = _edc_taps(param, Fs)
 
     logg.info("Running CD compensation...")
     logg.info(f"CD filter length: {K} taps, FFT size: {Nfft}")
@@ -85,14 +109,9 @@ def edc(sigIn, param):
     d_raw = _to_device(torch, host.view(np.float32 if host.dtype == np.complex64 else np.float64))
     d_x = torch.empty((nModes, Nsig, 2), dtype=torch.float32, device="cuda")
     d_y = torch.empty_like(d_x)
-    d_h = _to_device(torch, h.view(np.float32))
-    ws_bytes = int(lib.ocb_edc_workspace_bytes(Nsig, nModes, K))
-    d_ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
-    ws_ptr = (d_ws.data_ptr() + 255) // 256 * 256
     _cabi.check(lib.ocb_pack_fields(_ptr(d_raw), _engine.dtype_tag(host.dtype), Nsig, nModes, 0, _ptr(d_x), st),
                 "ocb_pack_fields")
-    _cabi.check(lib.ocb_edc_run(_ptr(d_x), _ptr(d_y), Nsig, nModes, _ptr(d_h), K, _vp(ws_ptr), ws_bytes, st),
-                "ocb_edc_run")
+    keep = edc_rows_device(d_x, d_y, h)
     _cabi.check(lib.ocb_unpack_fields(_ptr(d_y), Nsig, nModes, 0, _ptr(d_raw), _engine.dtype_tag(host.dtype), st),
                 "ocb_unpack_fields")
     out = d_raw.cpu().numpy().view(host.dtype).reshape(Nsig, nModes)
@@ -229,15 +248,53 @@ def _run_equalizer_batch(setups):
                                          _cabi.OCB_C64, arr.size, st), "ocb_cast_complex")
         return raw  # keep alive until the stream has consumed it
 
+    def upload_stack(arrs, dst):
+        """ONE pinned staging buffer and ONE H2D copy for the whole batch (the streams share shape and dtype), one
+        cast kernel to complex64, then a device-side strided copy into the per-stream slices of ``dst``."""
+        dt = arrs[0].dtype
+        n0 = arrs[0].shape[0]
+        if any(a.dtype != dt or a.shape != arrs[0].shape for a in arrs):
+            return [upload_c64(a, dst[i]) for i, a in enumerate(arrs)]
+        ft = np.float32 if dt == np.complex64 else np.float64
+        stage = torch.empty((len(arrs), n0, nM, 2), dtype=torch.float32 if dt == np.complex64 else torch.float64,
+                            pin_memory=True)
+        view = stage.numpy()
+        for i, a in enumerate(arrs):
+            view[i] = a.view(ft).reshape(n0, nM, 2)
+        raw = stage.to("cuda", non_blocking=True)
+        if dt == np.complex64:
+            dst.copy_(raw)
+            return [stage, raw]
+        c64 = torch.empty((len(arrs), n0, nM, 2), dtype=torch.float32, device="cuda")
+        _cabi.check(lib.ocb_cast_complex(_ptr(raw), _cabi.OCB_C128, _ptr(c64), _cabi.OCB_C64, len(arrs) * n0 * nM, st),
+                    "ocb_cast_complex")
+        dst.copy_(c64)
+        return [stage, raw, c64]
+
     d_x = torch.zeros((nS, nSamp, nM, 2), dtype=torch.float32, device="cuda")  # zero rows = the padding
-    keep = [upload_c64(s.sig, d_x[i, s.Lpad:s.Lpad + s.sig.shape[0]]) for i, s in enumerate(setups)]
+    nsig = s0.sig.shape[0]
+    keep = upload_stack([s.sig for s in setups], d_x[:, s0.Lpad:s0.Lpad + nsig])
     if has_ref:
         d_ref = torch.empty((nS, Lref, nM, 2), dtype=torch.float32, device="cuda")
-        keep += [upload_c64(np.ascontiguousarray(s.symbRef[:Lref]), d_ref[i]) for i, s in enumerate(setups)]
+        keep += upload_stack([np.ascontiguousarray(s.symbRef[:Lref]) for s in setups], d_ref)
     else:
         d_ref = None
     d_H = _to_device(torch, np.stack([s.H for s in setups]).view(np.float32))
     d_Hw = _to_device(torch, np.stack([s.H_ for s in setups]).view(np.float32)) if s0.runWL else None
+    d_y, d_e, hiter = equalizer_stages_device(s0, nS, d_x, d_ref, Lref, d_H, d_Hw)
+    return _equalizer_download(setups, d_y, d_e, d_H, d_Hw, hiter)
+
+
+def equalizer_stages_device(s0, nS, d_x, d_ref, Lref, d_H, d_Hw):
+    """Device-resident equalizer: run every stage of ``s0.alg`` on ``d_x`` (nS, nPad, nModes, 2) float32 CUDA (already
+    zero-padded by floor(nTaps/2) rows on both ends) with taps ``d_H`` / ``d_Hw`` updated in place.  Returns
+    (d_y (nS, totalNumSymb, nModes, 2), d_e (nS, nModes, totalNumSymb), Hiter tensor or None).  No host sync."""
+    torch = _cabi.require_cuda()
+    lib = _cabi.lib()
+    st = _vp(_cabi.stream_ptr(torch))
+    nM, nT, SpS = s0.nModes, s0.nTaps, s0.SpS
+    nSamp = int(d_x.shape[1])
+    total = s0.totalNumSymb
     d_c = _to_device(torch, s0.constSymb.view(np.float32))
     d_r = _to_device(torch, s0.Rrde)
     d_y = torch.zeros((nS, total, nM, 2), dtype=torch.float32, device="cuda")
@@ -289,7 +346,12 @@ def _run_equalizer_batch(setups):
             )
             hiter = d_hit
         nStart = nEnd
+    return d_y, d_e, hiter
 
+
+def _equalizer_download(setups, d_y, d_e, d_H, d_Hw, hiter):
+    s0 = setups[0]
+    nS, nM, nT, total = len(setups), s0.nModes, s0.nTaps, s0.totalNumSymb
     y = d_y.cpu().numpy().view(np.complex64).reshape(nS, total, nM)
     e = d_e.cpu().numpy()
     H = d_H.cpu().numpy().view(np.complex64).reshape(nS, nM * nM, nT)

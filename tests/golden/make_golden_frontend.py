@@ -80,5 +80,38 @@ G["sync_tx_real"] = tx_real
 G["sync_real"] = symbolSync(rxs.copy(), tx_real.copy(), 2, "real")
 G["sync_amp_1d"] = symbolSync(rxs[:, 0].copy(), np.roll(txs[:, 0], 9), 2, "amp")
 
+# pdmCoherentReceiver (ideal photodiodes) and delaySignal: a 2-pol field with a frequency-shifted, phase-noisy LO
+from optic.dsp.core import delaySignal  # noqa: E402
+from optic.models.devices import basicLaserModel, pdmCoherentReceiver  # noqa: E402
+
+nfe = 1 << 13
+Fs_fe = 64e9
+Es = (rng.normal(size=(nfe, 2)) + 1j * rng.normal(size=(nfe, 2))) * np.sqrt(1e-3 / 4)
+Es = np.fft.ifft(np.fft.fft(Es, axis=0) * (np.abs(np.fft.fftfreq(nfe)) < 0.3)[:, None], axis=0)
+pl = parameters()
+pl.P, pl.lw, pl.RIN_var, pl.Ns, pl.Fs, pl.seed, pl.freqShift = 10, 100e3, 0, nfe, Fs_fe, 789, 1.5e9
+Elo = basicLaserModel(pl)
+G["fe_Es"], G["fe_Elo"] = Es, Elo
+ppd = parameters()
+ppd.B, ppd.Fs, ppd.ideal, ppd.seed = 32e9, Fs_fe, True, 1011
+pfe = parameters()
+pfe.Fs, pfe.polRotation, pfe.pdl, pfe.polDelay = Fs_fe, np.pi / 3, 0, 0
+G["fe_rot"] = pdmCoherentReceiver(Es, Elo, pfe, ppd)
+pfe = parameters()
+pfe.Fs, pfe.polRotation, pfe.pdl, pfe.polDelay = Fs_fe, 0.4, 1.5, 0
+pfe.phaseImbX, pfe.phaseImbY, pfe.ampImbX, pfe.ampImbY = 3 * np.pi / 180, -2 * np.pi / 180, 0.5, -0.3
+ppd.R = 0.8
+G["fe_imb"] = pdmCoherentReceiver(Es, Elo, pfe, ppd)
+ppd.R = 1
+pfe = parameters()
+pfe.Fs, pfe.polRotation, pfe.pdl, pfe.polDelay = Fs_fe, np.pi / 3, 0, 3 / 32e9   # the notebook's front end
+G["fe_delay"] = pdmCoherentReceiver(Es, Elo, pfe, ppd)
+pfe = parameters()
+pfe.Fs, pfe.polRotation, pfe.timeSkewX, pfe.timeSkewY = Fs_fe, 0.2, 4e-12, -6e-12
+G["fe_skew"] = pdmCoherentReceiver(Es, Elo, pfe, ppd)
+G["fe_1pol"] = pdmCoherentReceiver(Es[:, 0].copy(), Elo, pfe, ppd)
+G["delay_c"] = delaySignal(Es[:, 0].copy(), 7.3e-12, Fs_fe)
+G["delay_r"] = delaySignal(Es[:, 1].real.copy(), -2.6e-11, Fs_fe)
+
 np.savez_compressed(OUT, **G)
 print({k: (v.shape, v.dtype) for k, v in G.items()})

@@ -74,3 +74,22 @@ def test_symbol_sync_matches_reference(g):
     tx0 = np.roll(g["sync_tx_amp"][:, 1], 11)          # the generator built column 1 as roll(tx0, -11)
     y = fe.symbol_sync(g["sync_rx"][:, 0], np.roll(tx0, 9), 2, "amp")
     assert y.shape == g["sync_amp_1d"].shape and np.array_equal(y, g["sync_amp_1d"])
+
+
+def test_pdm_frontend_and_delay_match_reference(g):
+    """pdmCoherentReceiver with ideal photodiodes and delaySignal: oracle against the unmodified reference."""
+    Es, Elo, Fs = g["fe_Es"], g["fe_Elo"], 64e9
+    y = fe.pdm_coherent_receiver_ideal(Es, Elo, Fs, polRotation=np.pi / 3)
+    assert np.allclose(y, g["fe_rot"], rtol=0, atol=1e-12 * np.abs(g["fe_rot"]).max())
+    y = fe.pdm_coherent_receiver_ideal(Es, Elo, Fs, polRotation=0.4, pdl=1.5, phaseImb=(3 * np.pi / 180, -2 * np.pi / 180),
+                                       ampImb=(0.5, -0.3), R=0.8)
+    assert np.allclose(y, g["fe_imb"], rtol=0, atol=1e-12 * np.abs(g["fe_imb"]).max())
+    y = fe.pdm_coherent_receiver_ideal(Es, Elo, Fs, polRotation=np.pi / 3, polDelay=3 / 32e9)
+    assert np.allclose(y, g["fe_delay"], rtol=0, atol=1e-10 * np.abs(g["fe_delay"]).max())
+    y = fe.pdm_coherent_receiver_ideal(Es, Elo, Fs, polRotation=0.2, timeSkew=(4e-12, -6e-12))
+    assert np.allclose(y, g["fe_skew"], rtol=0, atol=1e-10 * np.abs(g["fe_skew"]).max())
+    y = fe.pdm_coherent_receiver_ideal(Es[:, 0], Elo, Fs, polRotation=0.2, timeSkew=(4e-12, -6e-12))
+    assert np.allclose(y, g["fe_1pol"], rtol=0, atol=1e-10 * np.abs(g["fe_skew"]).max())
+    assert np.allclose(fe.delay_signal(Es[:, 0], 7.3e-12, Fs), g["delay_c"], rtol=0, atol=1e-12)
+    yr = fe.delay_signal(Es[:, 1].real, -2.6e-11, Fs)
+    assert np.isrealobj(yr) and np.allclose(yr, g["delay_r"], rtol=0, atol=1e-12)
