@@ -320,7 +320,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spans", type=int, default=10, help="spans per propagation (10 = cfg2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the NL-kernel microbench and the CuPy stand-in")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extras: NL-kernel microbench, CuPy stand-in, cfg1, rx_chain (cfg3), cfg4_dbp, cfg5_mc")
     ap.add_argument("--nl-only", action="store_true", help="only time the standalone nonlinear-step kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -437,6 +438,16 @@ def main():
     e2e_value = N_SAMPLES * e2e_steps * world / float(te.item()) / 1e6
     noise_bytes = N_SAMPLES * 8  # injected ASE realisation (seeded reference mode)
 
+    sharded = {}
+    if not args.no_extras:
+        import bench_extras as bx
+        for name, fn in (("cfg4_dbp", bx.extra_cfg4_dbp), ("cfg5_mc", bx.extra_cfg5_mc)):
+            try:
+                sharded[name] = fn(torch, dist, world, rank)
+            except Exception as e:
+                sharded[name] = {"error": f"{type(e).__name__}: {e}"}
+                if world > 1:
+                    raise  # a rank that drops out of a collective would hang the others
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         mean_I = tot_iters / max(1, tot_steps)
@@ -488,6 +499,14 @@ def main():
             sr, si = cupy_standin_rate(torch, rows0, channel_param(1))
             line["cupy_standin"] = {"value": sr, "unit": "Msamples/s", "mean_iterations": si,
                                     "what": "op-for-op torch.fft restatement of optic/models/modelsGPU.py:428-482 (unfused, host sync per iteration), 40 steps, complex64, same B200"}
+        line.update(sharded)
+        if not args.no_extras and world == 1:
+            import bench_extras as bx
+            for name, fn in (("cfg1", lambda: bx.extra_cfg1(torch)), ("rx_chain", lambda: bx.extra_rx_chain(torch, peak))):
+                try:
+                    line[name] = fn()
+                except Exception as e:  # an extra must never take the headline down
+                    line[name] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_cpu_baseline:
             rate, s_, dt, kind = reference_rate(4)
             line["cpu_baseline"] = {"value": rate, "unit": "Msamples/s", "cores": 1, "kind": kind,

@@ -59,7 +59,12 @@ def pdm_frontend_rows_device(d_Es, paramFE, d_Elo=None, lo_power_w=0.0, lo_freq_
                                          float(polRotation), float(pdl), float(R), float(lo_power_w), float(lo_freq_shift),
                                          float(Fs), iq, st), "ocb_pdm_frontend_run")
     for p, sk in enumerate(skew):
-        if sk != 0:  # iqMixing skew (core.py:962-965): I delayed by -sk/2, Q by +sk/2, each as a real signal
+        if sk == 0:
+            # Reference quirk (reproduced): iqMixing ALWAYS passes I and Q through delaySignal (core.py:962-965), and a
+            # zero delay is not the identity there — the 512-tap "delta" sits one tap off the compensated group delay
+            # and the final roll(-1) wraps the leading zero to the end — so the LAST sample of each output is zero.
+            d_S[p, N - 1] = 0
+        else:  # iqMixing skew (core.py:962-965): I delayed by -sk/2, Q by +sk/2, each as a real signal
             s = d_S[p]
             re = torch.stack([s[:, 0], torch.zeros_like(s[:, 0])], dim=1)[None].contiguous()
             im = torch.stack([s[:, 1], torch.zeros_like(s[:, 1])], dim=1)[None].contiguous()

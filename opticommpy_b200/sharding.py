@@ -93,3 +93,40 @@ def run_sharded(fn, units, *args, **kwargs):
     mine = shard_units(len(units))
     local = {i: fn(units[i], *args, **kwargs) for i in mine}
     return gather_results(local, len(units))
+
+
+def gather_device(local: dict, n_units: int):
+    """All-gather per-unit CUDA tensors WITHOUT a host round trip: ``local`` maps unit index -> tensor (same shape and
+    dtype for every unit; complex allowed).  Ragged ownership is padded to the largest shard; one ``all_gather`` over
+    NCCL / NVLink.  Returns the list of ``n_units`` tensors (views into the gathered buffers) on every rank."""
+    import torch
+
+    d = _dist()
+    rank, ws = world()
+    mine = shard_units(n_units, rank, ws)
+    assert sorted(local) == mine, "local results do not match this rank's shard"
+    if d is None or ws == 1:
+        return [local[i] for i in range(n_units)]
+    per_rank = -(-n_units // ws)
+    sample = local[mine[0]] if mine else None
+    meta = [tuple(sample.shape), str(sample.dtype)] if rank == 0 else None
+    box = [meta]
+    d.broadcast_object_list(box, src=0)
+    shape, dtype = box[0][0], getattr(torch, box[0][1].split(".")[-1])
+    if sample is not None:
+        dev = sample.device
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if d.get_backend() == "nccl" else torch.device("cpu")
+    send = torch.zeros((per_rank,) + tuple(shape), dtype=dtype, device=dev)
+    for j, i in enumerate(mine):
+        send[j].copy_(local[i])
+    is_complex = send.is_complex()
+    flat = torch.view_as_real(send) if is_complex else send
+    recv = [torch.empty_like(flat) for _ in range(ws)]
+    d.all_gather(recv, flat.contiguous())
+    out = [None] * n_units
+    for r in range(ws):
+        block = torch.view_as_complex(recv[r]) if is_complex else recv[r]
+        for j, i in enumerate(shard_units(n_units, r, ws)):
+            out[i] = block[j]
+    return out

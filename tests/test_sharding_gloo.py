@@ -41,6 +41,13 @@ def _worker(rank, world, port, n_units, q):
     full = sharding.gather_results(local, n_units)
     ref = [work(units[i], 100 + i) for i in range(n_units)]
     ok = all(np.array_equal(a, b) for a, b in zip(full, ref)) and len(full) == n_units
+    # the device-side gather (no numpy round trip; CPU tensors under gloo, CUDA tensors under NCCL): ragged / empty shards
+    tl = {i: torch.from_numpy(local[i].astype(np.complex64)) for i in mine}
+    tfull = sharding.gather_device(tl, n_units)
+    ok = ok and len(tfull) == n_units and all(np.array_equal(t.numpy(), r.astype(np.complex64)) for t, r in zip(tfull, ref))
+    sc = {i: torch.tensor([float(i), 2.0 * i, -1.0], dtype=torch.float64) for i in mine}   # three scalars per unit (cfg5)
+    sfull = sharding.gather_device(sc, n_units)
+    ok = ok and all(s.tolist() == [float(i), 2.0 * i, -1.0] for i, s in enumerate(sfull))
     q.put((rank, mine, ok))
     dist.barrier()
     dist.destroy_process_group()
