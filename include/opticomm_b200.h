@@ -219,9 +219,12 @@ int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hwl, void* y,
  * decision_directed = 1) training stage.  Replaces coreAdaptEq with rlsUp / ddrlsUp
  * (optic/dsp/equalization.py:354-516, 576-644, 712-785).  Same buffer conventions as ocb_mimo_eq_run; the
  * inverse correlation matrices start from the identity in every call (like the reference's 'rls' branch,
- * :447-451) and live on the device only.  nTaps <= 32.  workspace: the gain vectors Y_N(s),
- * ocb_mimo_eq_rls_workspace_bytes(nStreams, nModes, L) bytes.                                              */
-int64_t ocb_mimo_eq_rls_workspace_bytes(int nStreams, int nModes, int64_t L);
+ * :447-451) and live on the device only.  nTaps <= 64 (one matrix row per lane up to 32 taps, two beyond;
+ * examples/test_WDM_transmission.ipynb uses 35).  'rls' is pinned to reference golden vectors (nTaps = 11 and 35);
+ * 'dd-rls' is pinned to the CPU oracle ONLY: the reference initialises the inverse correlation matrix for
+ * alg == 'rls' alone (:447-451), so its own 'dd-rls' stage runs on an uninitialised matrix and cannot produce golden
+ * vectors.  workspace: the gain vectors Y_N(s), ocb_mimo_eq_rls_workspace_bytes(nStreams, nModes, L, nTaps) bytes.  */
+int64_t ocb_mimo_eq_rls_workspace_bytes(int nStreams, int nModes, int64_t L, int nTaps);
 int ocb_mimo_eq_rls_run(const void* x, const void* ref, void* H, void* y, void* errSq, void* Hiter,
                         int nStreams, int64_t nSamp, int64_t x_stream_stride, int64_t ref_stream_stride,
                         int64_t y_stream_stride, int64_t err_stream_stride, int64_t err_mode_stride,

@@ -67,7 +67,7 @@ SIGNATURES = {
     "ocb_ssfm_plan_engine": (_i, [_vp]),
     "ocb_ssfm_plan_profile": (_i, [_vp, _i]),
     "ocb_ssfm_plan_profile_read": (_i, [_vp, C.POINTER(C.c_double)]),
-    "ocb_mimo_eq_rls_workspace_bytes": (_i64, [_i, _i, _i64]),
+    "ocb_mimo_eq_rls_workspace_bytes": (_i64, [_i, _i, _i64, _i]),
     "ocb_mimo_eq_rls_run": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i, _i, _i, _i,
                                 C.c_float, _vp, _i, _vp, _i64, _vp]),
     "ocb_pnorm_run": (_i, [_vp, _i64, _vp, _i64, _vp]),

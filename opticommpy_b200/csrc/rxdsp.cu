@@ -448,9 +448,9 @@ int launch_mimo(bool wl, cudaStream_t st, const float2* X, const float2* REF, fl
 
 }  // namespace
 
-extern "C" int64_t ocb_mimo_eq_rls_workspace_bytes(int nStreams, int nModes, int64_t L) {
-    if (nStreams <= 0 || nModes <= 0 || L < 0) return -1;
-    return (int64_t)nStreams * nModes * L * 32 * (int64_t)sizeof(float2) + 256;
+extern "C" int64_t ocb_mimo_eq_rls_workspace_bytes(int nStreams, int nModes, int64_t L, int nTaps) {
+    if (nStreams <= 0 || nModes <= 0 || L < 0 || nTaps < 1 || nTaps > 64) return -1;
+    return (int64_t)nStreams * nModes * L * (nTaps <= 32 ? 32 : 64) * (int64_t)sizeof(float2) + 256;
 }
 
 extern "C" int ocb_mimo_eq_rls_run(const void* x, const void* ref, void* H, void* y, void* errSq, void* Hiter,
@@ -462,12 +462,12 @@ extern "C" int ocb_mimo_eq_rls_run(const void* x, const void* ref, void* H, void
     OCB_REQUIRE(x && H && y && errSq && workspace, "mimo_eq_rls_run: NULL argument");
     OCB_REQUIRE(nStreams > 0 && L >= 0 && nSamp > 0, "mimo_eq_rls_run: bad sizes");
     OCB_REQUIRE(nModes == 1 || nModes == 2 || nModes == 4, "mimo_eq_rls_run: nModes must be 1, 2 or 4");
-    OCB_REQUIRE(nTaps >= 1 && nTaps <= 32, "mimo_eq_rls_run: nTaps must be in [1, 32] (one matrix row per lane)");
+    OCB_REQUIRE(nTaps >= 1 && nTaps <= 64, "mimo_eq_rls_run: nTaps must be in [1, 64] (one or two matrix rows per lane)");
     OCB_REQUIRE(SpS >= 1 && lambda > 0.f, "mimo_eq_rls_run: SpS must be >= 1 and lambda > 0");
     OCB_REQUIRE(L == 0 || (L - 1) * SpS + nTaps <= nSamp, "mimo_eq_rls_run: window runs past the end of the input");
     if (decision_directed) OCB_REQUIRE(constSymb && M >= 1, "mimo_eq_rls_run: constellation required for dd-rls");
     else OCB_REQUIRE(ref != nullptr, "mimo_eq_rls_run: reference symbols required for rls");
-    OCB_REQUIRE(workspace_bytes >= ocb_mimo_eq_rls_workspace_bytes(nStreams, nModes, L), "mimo_eq_rls_run: workspace too small");
+    OCB_REQUIRE(workspace_bytes >= ocb_mimo_eq_rls_workspace_bytes(nStreams, nModes, L, nTaps), "mimo_eq_rls_run: workspace too small");
     if (L == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
 #define OCB_RLS_CASE(NM_)                                                                                          \

@@ -12,7 +12,9 @@
 //   k_mimo_eq_rls : one warp per (stream, output mode): the tap recurrence with the precomputed gain vectors.
 // Sd starts from the identity in every stage call, like the reference (equalization.py:447-451 — the reference
 // leaves Sd undefined for 'dd-rls'; the identity is used here for both).
-// Limits: nTaps <= 32 (one tap / one matrix row per lane).  Included by rxdsp.cu inside its anonymous namespace.
+// nTaps <= 32: one tap / one matrix row per lane, the row also in registers.  32 < nTaps <= 64 (RPL = 2, e.g. the 35 taps
+// of examples/test_WDM_transmission.ipynb): lane i owns rows / taps i and i + 32 and the matrix lives in shared memory
+// only (k_rls_gain2).  Included by rxdsp.cu inside its anonymous namespace.
 #pragma once
 
 __device__ __forceinline__ float2 cdiv(float2 a, float2 b) {  // a / b
@@ -77,8 +79,78 @@ k_rls_gain(const float2* __restrict__ X, float2* __restrict__ G, int64_t xStride
     }
 }
 
+// 32 < nTaps <= 64: two rows per lane (r = lane + 32 k), Sd in shared memory only (row stride 65: conflict-free row and
+// column walks).  Same recursion, same order of operations per matrix entry as k_rls_gain.
+template <int NM>
+__global__ void __launch_bounds__(32)
+k_rls_gain2(const float2* __restrict__ X, float2* __restrict__ G, int64_t xStride, int64_t L, int nTaps, int SpS,
+            float lambda) {
+    constexpr int T = 64, STR = 65;
+    extern __shared__ float2 rls_smem[];
+    float2* Ss = rls_smem;            // [T][STR]
+    float2* su = Ss + T * STR;        // [T]
+    float2* sB = su + T;              // [T]
+    const int lane = threadIdx.x;
+    const int stream = blockIdx.x / NM, N = blockIdx.x % NM;
+    const float2* x = X + (int64_t)stream * xStride;
+    float2* g = G + ((int64_t)stream * NM + N) * L * T;
+    for (int k = 0; k < 2; ++k) {
+        const int r = lane + 32 * k;
+        for (int j = 0; j < T; ++j) Ss[r * STR + j] = make_float2((j == r && r < nTaps) ? 1.f : 0.f, 0.f);
+    }
+    const float inv_lambda = 1.0f / lambda;
+    __syncwarp();
+    for (int64_t s = 0; s < L; ++s) {
+        float2 ui[2];
+        for (int k = 0; k < 2; ++k) {
+            const int r = lane + 32 * k;
+            float2 xi = make_float2(0.f, 0.f);
+            if (r < nTaps) xi = x[(s * SpS + r) * NM + N];
+            ui[k] = make_float2(xi.x, -xi.y);  // u = conj(x)
+            su[r] = ui[k];
+        }
+        __syncwarp();
+        float2 A[2], B[2];
+        float2 c = make_float2(0.f, 0.f);
+        for (int k = 0; k < 2; ++k) {
+            const int r = lane + 32 * k;
+            A[k] = make_float2(0.f, 0.f);
+            B[k] = make_float2(0.f, 0.f);
+            for (int j = 0; j < T; ++j) {
+                const float2 uj = su[j];
+                const float2 a = cmul(Ss[r * STR + j], uj);
+                A[k].x += a.x; A[k].y += a.y;
+                const float2 b = cmul_conj(Ss[j * STR + r], uj);
+                B[k].x += b.x; B[k].y += b.y;
+            }
+            const float2 ck = cmul_conj(A[k], ui[k]);
+            c.x += ck.x; c.y += ck.y;
+        }
+        c.x = warp_sum(c.x); c.y = warp_sum(c.y);
+        const float2 den = make_float2(lambda + c.x, c.y);
+        sB[lane] = B[0];
+        sB[lane + 32] = B[1];
+        __syncwarp();  // every lane has read its columns of Ss; B is visible
+        for (int k = 0; k < 2; ++k) {
+            const int r = lane + 32 * k;
+            const float2 Ad = cdiv(A[k], den);
+            float2 Yv = make_float2(0.f, 0.f);
+            for (int j = 0; j < T; ++j) {
+                const float2 rr = cmul(Ad, sB[j]);
+                const float2 o = Ss[r * STR + j];
+                const float2 nv = make_float2((o.x - rr.x) * inv_lambda, (o.y - rr.y) * inv_lambda);
+                Ss[r * STR + j] = nv;
+                const float2 y = cmul(nv, su[j]);
+                Yv.x += y.x; Yv.y += y.y;
+            }
+            g[s * T + r] = Yv;
+        }
+        __syncwarp();
+    }
+}
+
 // One warp per (stream, output mode m); lane = tap.  DD: decision-directed error (dd-rls), else reference symbols.
-template <int NM, bool DD>
+template <int NM, bool DD, int RPL>
 __global__ void __launch_bounds__(32 * NM)
 k_mimo_eq_rls(const float2* __restrict__ X, const float2* __restrict__ REF, const float2* __restrict__ G,
               float2* __restrict__ Hg, float2* __restrict__ Y, float* __restrict__ ERR, float2* __restrict__ HIT,
@@ -88,25 +160,33 @@ k_mimo_eq_rls(const float2* __restrict__ X, const float2* __restrict__ REF, cons
     const int stream = blockIdx.x;
     const float2* x = X + (int64_t)stream * xStride;
     const float2* ref = REF ? REF + (int64_t)stream * refStride : nullptr;
-    const float2* g = G + (int64_t)stream * NM * L * 32;
+    constexpr int GS = 32 * RPL;  // gain-vector stride per symbol
+    const float2* g = G + (int64_t)stream * NM * L * GS;
     float2* Hs = Hg + (int64_t)stream * NM * NM * nTaps;
     float2* y = Y + (int64_t)stream * yStride;
     float* err = ERR + (int64_t)stream * errStride + (int64_t)m * errModeStride;
     float2* hit = HIT ? HIT + (int64_t)stream * L * NM * NM * nTaps : nullptr;
-    const bool live = lane < nTaps;
-    float2 H[NM];
+    float2 H[NM][RPL];
 #pragma unroll
-    for (int n = 0; n < NM; ++n) H[n] = live ? Hs[(m + n * NM) * nTaps + lane] : make_float2(0.f, 0.f);
+    for (int n = 0; n < NM; ++n)
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const int t = lane + 32 * k;
+            H[n][k] = t < nTaps ? Hs[(m + n * NM) * nTaps + t] : make_float2(0.f, 0.f);
+        }
     for (int64_t s = 0; s < L; ++s) {
         float2 o = make_float2(0.f, 0.f);
-        float2 gy[NM];
+        float2 gy[NM][RPL];
 #pragma unroll
-        for (int n = 0; n < NM; ++n) {
-            const float2 w = live ? x[(s * SpS + lane) * NM + n] : make_float2(0.f, 0.f);
-            gy[n] = g[((int64_t)n * L + s) * 32 + lane];
-            const float2 pr = cmul(H[n], w);  // equalization.py:464-468
-            o.x += pr.x; o.y += pr.y;
-        }
+        for (int n = 0; n < NM; ++n)
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                const int t = lane + 32 * k;
+                const float2 w = t < nTaps ? x[(s * SpS + t) * NM + n] : make_float2(0.f, 0.f);
+                gy[n][k] = g[((int64_t)n * L + s) * GS + t];
+                const float2 pr = cmul(H[n][k], w);  // equalization.py:464-468
+                o.x += pr.x; o.y += pr.y;
+            }
         o.x = warp_sum(o.x); o.y = warp_sum(o.y);
         float2 target;
         if constexpr (DD) {  // nearest constellation point, first index on ties (:751-753)
@@ -133,27 +213,40 @@ k_mimo_eq_rls(const float2* __restrict__ X, const float2* __restrict__ REF, cons
             err[s] = cabs2(e);
         }
 #pragma unroll
-        for (int n = 0; n < NM; ++n) {
-            const float2 u = cmul(e, gy[n]);  // H[m + n nModes, :] += err_m Y_n   (:641)
-            H[n].x += u.x; H[n].y += u.y;
-        }
-        if (hit && live) {
+        for (int n = 0; n < NM; ++n)
 #pragma unroll
-            for (int n = 0; n < NM; ++n) hit[(s * NM * NM + m + n * NM) * nTaps + lane] = H[n];
+            for (int k = 0; k < RPL; ++k) {
+                const float2 u = cmul(e, gy[n][k]);  // H[m + n nModes, :] += err_m Y_n   (:641)
+                H[n][k].x += u.x; H[n][k].y += u.y;
+            }
+        if (hit) {
+#pragma unroll
+            for (int n = 0; n < NM; ++n)
+#pragma unroll
+                for (int k = 0; k < RPL; ++k)
+                    if (lane + 32 * k < nTaps) hit[(s * NM * NM + m + n * NM) * nTaps + lane + 32 * k] = H[n][k];
         }
     }
-    if (live) {
 #pragma unroll
-        for (int n = 0; n < NM; ++n) Hs[(m + n * NM) * nTaps + lane] = H[n];
-    }
+    for (int n = 0; n < NM; ++n)
+#pragma unroll
+        for (int k = 0; k < RPL; ++k)
+            if (lane + 32 * k < nTaps) Hs[(m + n * NM) * nTaps + lane + 32 * k] = H[n][k];
 }
 
 template <int NM>
 int launch_rls(cudaStream_t st, const float2* X, const float2* REF, float2* G, float2* H, float2* Y, float* ERR,
                float2* HIT, int nStreams, int64_t xs, int64_t rs, int64_t ys, int64_t es, int64_t ems, int64_t L,
                int nTaps, int SpS, bool dd, float lambda, const float2* cs, int M) {
-    OCB_LAUNCH((k_rls_gain<NM>), nStreams * NM, 32, 0, st, X, G, xs, L, nTaps, SpS, lambda);
-    if (dd) OCB_LAUNCH((k_mimo_eq_rls<NM, true>), nStreams, 32 * NM, 0, st, X, REF, G, H, Y, ERR, HIT, xs, rs, ys, es, ems, L, nTaps, SpS, cs, M);
-    else OCB_LAUNCH((k_mimo_eq_rls<NM, false>), nStreams, 32 * NM, 0, st, X, REF, G, H, Y, ERR, HIT, xs, rs, ys, es, ems, L, nTaps, SpS, cs, M);
+    if (nTaps <= 32) {
+        OCB_LAUNCH((k_rls_gain<NM>), nStreams * NM, 32, 0, st, X, G, xs, L, nTaps, SpS, lambda);
+        if (dd) OCB_LAUNCH((k_mimo_eq_rls<NM, true, 1>), nStreams, 32 * NM, 0, st, X, REF, G, H, Y, ERR, HIT, xs, rs, ys, es, ems, L, nTaps, SpS, cs, M);
+        else OCB_LAUNCH((k_mimo_eq_rls<NM, false, 1>), nStreams, 32 * NM, 0, st, X, REF, G, H, Y, ERR, HIT, xs, rs, ys, es, ems, L, nTaps, SpS, cs, M);
+        return 0;
+    }
+    const size_t smem = (size_t)(64 * 65 + 128) * sizeof(float2);  // 34 KB: below the 48 KB default limit
+    OCB_LAUNCH((k_rls_gain2<NM>), nStreams * NM, 32, smem, st, X, G, xs, L, nTaps, SpS, lambda);
+    if (dd) OCB_LAUNCH((k_mimo_eq_rls<NM, true, 2>), nStreams, 32 * NM, 0, st, X, REF, G, H, Y, ERR, HIT, xs, rs, ys, es, ems, L, nTaps, SpS, cs, M);
+    else OCB_LAUNCH((k_mimo_eq_rls<NM, false, 2>), nStreams, 32 * NM, 0, st, X, REF, G, H, Y, ERR, HIT, xs, rs, ys, es, ems, L, nTaps, SpS, cs, M);
     return 0;
 }

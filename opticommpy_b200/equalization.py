@@ -210,8 +210,8 @@ def _parse_equalizer_args(sigIn, param, symbRef):
         raise TypeError("param.alg must be a list of algorithm names, e.g. ['cma', 'rde']")
     for a in s.alg:
         if a in ("rls", "dd-rls"):
-            if s.nTaps > 32:
-                raise NotImplementedError("'rls'/'dd-rls' on the GPU keep one matrix row per lane: nTaps <= 32")
+            if s.nTaps > 64:
+                raise NotImplementedError("'rls'/'dd-rls' on the GPU keep at most two matrix rows per lane: nTaps <= 64")
             if s.runWL:
                 raise NotImplementedError("'rls'/'dd-rls' have no widely-linear update in the reference (rlsUp ignores H_)")
             continue
@@ -316,7 +316,7 @@ def equalizer_stages_device(s0, nS, d_x, d_ref, Lref, d_H, d_Hw):
             if s0.storeCoeff:
                 d_hit = torch.empty((nS, Ls, nM * nM, nT, 2), dtype=torch.float32, device="cuda")
             if name in ("rls", "dd-rls"):
-                ws_bytes = int(lib.ocb_mimo_eq_rls_workspace_bytes(nS, nM, Ls))
+                ws_bytes = int(lib.ocb_mimo_eq_rls_workspace_bytes(nS, nM, Ls, nT))
                 d_ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
                 ws_ptr = (d_ws.data_ptr() + 255) // 256 * 256
                 lam = float(np.float32(s0.lambdaRLS))  # the reference casts lambda to prec (:225)
@@ -388,7 +388,7 @@ def mimoAdaptEqualizer(sigIn, param=None, symbRef=None):
     returnResults [False], prec [np.complex64].
 
     Algorithms: 'cma', 'rde', 'nlms', 'dd-lms', 'da-rde', 'rls', 'dd-rls', 'static' (list form only; one
-    entry of ``L`` and ``mu`` per stage; 'rls'/'dd-rls': nTaps <= 32, forgetting factor ``lambdaRLS``, the inverse
+    entry of ``L`` and ``mu`` per stage; 'rls'/'dd-rls': nTaps <= 64, forgetting factor ``lambdaRLS``, the inverse
     correlation matrices start from the identity in every stage).  Returns ``sigOut`` or, with ``returnResults``,
     ``(sigOut, H, errSq, Hiter)`` / ``(sigOut, H, H_, errSq, Hiter)`` in widely-linear mode.
     """

@@ -53,5 +53,6 @@ def run(tag, **kw):
 run("rls", alg=["rls"], mu=[1e-3], L=[n], lambdaRLS=0.99)
 run("nlms_rls", alg=["nlms", "rls"], mu=[5e-3, 1e-3], L=[500, 1000], lambdaRLS=0.995)
 run("rls_store", alg=["rls"], mu=[1e-3], L=[400], lambdaRLS=0.98, storeCoeff=True)
+run("rls35", alg=["nlms", "rls"], mu=[5e-3, 1e-3], L=[300, 1200], lambdaRLS=0.995, nTaps=35)  # the notebook's tap count (> 32)
 np.savez_compressed(OUT, **G)
 print({k: (v.shape, v.dtype) for k, v in G.items()})

@@ -86,8 +86,9 @@ def test_equalizer_argument_parsing(golden):
     assert s.Rcma == pytest.approx(1.32, abs=1e-6)
     s = _parse_equalizer_args(golden["eq_in"], Bag(alg=["rls"], mu=[1e-3]), golden["eq_ref"])
     assert s.symbRef is not None and s.lambdaRLS == 0.99      # 'rls' trains against the reference symbols
-    with pytest.raises(NotImplementedError):                  # one matrix row per lane: nTaps <= 32
-        _parse_equalizer_args(golden["eq_in"], Bag(alg=["rls"], mu=[1e-3], nTaps=33), None)
+    _parse_equalizer_args(golden["eq_in"], Bag(alg=["rls"], mu=[1e-3], nTaps=35), None)  # two matrix rows per lane
+    with pytest.raises(NotImplementedError):                  # at most two matrix rows per lane: nTaps <= 64
+        _parse_equalizer_args(golden["eq_in"], Bag(alg=["rls"], mu=[1e-3], nTaps=65), None)
     with pytest.raises(NotImplementedError):                  # rlsUp has no widely-linear update
         _parse_equalizer_args(golden["eq_in"], Bag(alg=["dd-rls"], mu=[1e-3], runWL=True), None)
 

@@ -12,6 +12,7 @@ CASES = {
     "rls": dict(alg=("rls",), mu=(1e-3,), L=(1500,), lambdaRLS=0.99),
     "nlms_rls": dict(alg=("nlms", "rls"), mu=(5e-3, 1e-3), L=(500, 1000), lambdaRLS=0.995),
     "rls_store": dict(alg=("rls",), mu=(1e-3,), L=(400,), lambdaRLS=0.98, storeCoeff=True),
+    "rls35": dict(alg=("nlms", "rls"), mu=(5e-3, 1e-3), L=(300, 1200), lambdaRLS=0.995, nTaps=35),
 }
 
 
@@ -27,7 +28,8 @@ def rel(a, b):
 @pytest.mark.parametrize("tag", sorted(CASES))
 def test_rls_oracle_matches_reference(g, tag):
     from opticommpy_b200.modulation import grayMapping
-    y, H, _, err, Hiter = ro.mimo_adapt_equalizer(g["in"], g["ref"], grayMapping(16, "qam"), nTaps=11, SpS=2, **CASES[tag])
+    kw = dict(CASES[tag])
+    y, H, _, err, Hiter = ro.mimo_adapt_equalizer(g["in"], g["ref"], grayMapping(16, "qam"), nTaps=kw.pop("nTaps", 11), SpS=2, **kw)
     assert y.shape == g[f"{tag}_y"].shape
     assert rel(y, g[f"{tag}_y"]) < 2e-4          # complex64 matrix recursion in the reference vs float64 here
     assert rel(H, g[f"{tag}_H"]) < 2e-4
