@@ -128,7 +128,7 @@ def extra_rx_chain(torch, peak_gbs, nsym_log2=21, cpu_nsym_log2=15):
     pq = lambda n: Bag(nTaps=31, SpS=2, M=16, constType="qam", alg=["cma", "rde"], mu=[1e-3, 2e-4],
                        L=[int(0.2 * n), int(0.8 * n)], prgsBar=False)
     pc = Bag(alg="bps", M=16, constType="qam", N=25, B=64, runFOE=False)
-    rxChain(x[: 1 << 16], pe, pq(1 << 15), pc)  # warm-up: plan caches, allocator
+    rxChain(x, pe, pq(nsym), pc)  # warm-up at full size: cuFFT plan cache, caching allocator
     torch.cuda.synchronize()
     timing = {}
     t0 = time.perf_counter()

@@ -39,16 +39,16 @@ int launch_time_bulk(const TimeArgs& a, cudaStream_t st) {
     OCB_LAUNCH_PDL((k_time_bulk<NP, MODE>), grid, 256, TimeBulkCfg::SMEM_BYTES, st, pdl_enabled(), a);
     return 0;
 }
-// Time-pass kernel per mode (measured on the B200, profiles/r2_summary.md): the fixed-point iteration passes TM_ITER /
-// TM_ITERF at N1 = 1024 run on the persistent bulk-copy-fed kernel (fused_time_bulk.cuh: E_c, E_hd and P_ch arrive by
-// cp.async.bulk issued before the dependency wait), every other pass on the one-wave kernel.  OCB_TIME_KERNEL=plain /
-// bulk (read when a plan is created) forces one of them for every mode (A/B knob); all choices produce bit-identical
-// fields.  The knobs live in the plan: see read_engine_knobs().
+// Time-pass kernel: the one-wave kernel k_time (64-thread CTAs, 7 per SM) by default.  OCB_TIME_KERNEL=bulk (read when a
+// plan is created) selects the persistent bulk-copy-fed kernel of fused_time_bulk.cuh for N1 = 1024 (E_c, E_hd and P_ch
+// arrive by cp.async.bulk issued before the dependency wait).  Measured on the B200 (profiles/r2_summary.md): launched
+// back to back the bulk kernel is faster for the iteration passes (TM_ITERF 21 vs 26 us, TM_ITER 26.6 vs 27.5 us), but
+// inside the step loop — alternating with k_freq, cold instruction cache, no overlap of its 193 KB CTAs with the
+// neighbouring kernels — the one-wave kernel wins by 2-5 % of the whole step.  Both produce bit-identical fields.
 template <int NP, int MODE>
 int launch_time(int Q1, const TimeArgs& a, cudaStream_t st) {
     const int choice = a.kernel_choice;
-    if (Q1 == 32 && (choice == 1 || (choice == 0 && (MODE == TM_ITER || MODE == TM_ITERF))))
-        return launch_time_bulk<NP, MODE>(a, st);
+    if (Q1 == 32 && choice == 1) return launch_time_bulk<NP, MODE>(a, st);
     switch (Q1) {
         case 8: return launch_time_t<8, NP, MODE>(a, st);
         case 16: return launch_time_t<16, NP, MODE>(a, st);
@@ -56,9 +56,13 @@ int launch_time(int Q1, const TimeArgs& a, cudaStream_t st) {
     }
     return fail("fused engine: unsupported N1", __FILE__, __LINE__);
 }
-// W positions per k_freq tile when N2 = 1024: 4 for the TMA-fed kernel (fused_freq_tma.cuh, default), else 16 (128-byte
-// row segments, one 512-thread CTA per SM) or 8; OCB_FREQ_TMA=0 / OCB_FREQ_C are A/B knobs read when a plan is created.
-// All variants produce bit-identical fields (same arithmetic, different data path).
+// Frequency-pass kernel at N2 = 1024.  Default: k_freq<32, 16> — 128-byte row segments of the W tile by coalesced
+// streaming loads / stores, the tile's 128 KB operator slice by cp.async.bulk (TMA engine) before the dependency wait.
+// OCB_FREQ_TMA=1 (read when a plan is created): k_freq_tma (fused_freq_tma.cuh) — the tile itself through a CUtensorMap
+// (cp.async.bulk.tensor box loads and stores), four independent 128-thread groups per CTA.  Measured on the B200
+// (profiles/r2_summary.md): launched back to back both take 15.0 us; inside the step loop the tensor-map variant is 4 %
+// slower for the whole step (only half of its operator slice can be prefetched before the wait: 208 KB of shared memory),
+// so it is the option, not the default.  All variants produce bit-identical fields.
 int freq_c(const ocb_ssfm_plan* p) {
     if (p->q2 != 32) return kFreqC;
     return (p->knob_freq_tma && p->wmap_ok) ? FreqTmaCfg::C : p->knob_freq_c;
@@ -80,20 +84,20 @@ int launch_freq(ocb_ssfm_plan* p, const float2* LP, int NP, cudaStream_t st,
     const int N1 = 32 * p->q1, Q2 = p->q2;
     const int c = freq_c(p);
     if (Q2 == 32 && c == FreqTmaCfg::C) {
-        const bool lockstep = p->knob_freq_lockstep;
+        const bool lockstep = p->knob_freq_lockstep, st_tma = p->knob_freq_tma_store;
         if (first_time_on_device(ONCE_FREQ_BASE + 14)) {
-            OCB_CUDA(cudaFuncSetAttribute(k_freq_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FreqTmaCfg::SMEM_BYTES));
-            OCB_CUDA(cudaFuncSetAttribute(k_freq_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FreqTmaCfg::SMEM_BYTES));
+            OCB_CUDA(cudaFuncSetAttribute(k_freq_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FreqTmaCfg::SMEM_BYTES));
+            OCB_CUDA(cudaFuncSetAttribute(k_freq_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FreqTmaCfg::SMEM_BYTES));
+            OCB_CUDA(cudaFuncSetAttribute(k_freq_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FreqTmaCfg::SMEM_BYTES));
+            OCB_CUDA(cudaFuncSetAttribute(k_freq_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FreqTmaCfg::SMEM_BYTES));
         }
         const int tiles = NP * N1 / FreqTmaCfg::C;
         const int grid = tiles / FreqTmaCfg::GROUPS;  // 128 CTAs (dual-pol): every group of every CTA owns one tile
         OCB_REQUIRE(grid * FreqTmaCfg::GROUPS == tiles && grid <= kNumSMs, "k_freq_tma: unexpected tile count");
-        if (lockstep)
-            OCB_LAUNCH_PDL(k_freq_tma<true>, grid, 512, FreqTmaCfg::SMEM_BYTES, st, pdl_enabled(), p->wmap, LP, tw, N1, NP,
-                           flag, step_id, need_flag, need_id);
-        else
-            OCB_LAUNCH_PDL(k_freq_tma<false>, grid, 512, FreqTmaCfg::SMEM_BYTES, st, pdl_enabled(), p->wmap, LP, tw, N1, NP,
-                           flag, step_id, need_flag, need_id);
+        auto kern = lockstep ? (st_tma ? k_freq_tma<true, true> : k_freq_tma<true, false>)
+                             : (st_tma ? k_freq_tma<false, true> : k_freq_tma<false, false>);
+        OCB_LAUNCH_PDL(kern, grid, 512, FreqTmaCfg::SMEM_BYTES, st, pdl_enabled(), (const CUtensorMap*)p->wmap_dev, W, LP, tw,
+                       N1, NP, flag, step_id, need_flag, need_id);
         return 0;
     }
     if (c == 16 && Q2 == 32) return launch_freq_t<32, 16>(W, LP, tw, N1, NP, flag, step_id, need_flag, need_id, st);

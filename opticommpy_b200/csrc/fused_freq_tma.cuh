@@ -3,7 +3,9 @@
 // Same arithmetic as k_freq<32, C> (fused_kernels.cuh): for a tile of C = 4 adjacent W positions p (all 1024 rows of
 // one polarisation) FFT_N2 over n2 -> x linear operator -> IFFT_N2, in place.  The data path is different:
 //
-//  * The W buffer is described once per plan by a CUtensorMap over float32 [pol][n2][2*N1].  A tile is a strided
+//  * The W buffer is described once per plan by a CUtensorMap over float32 [pol][n2][2*N1], kept in GLOBAL memory (the
+//    plan's workspace) so that its address — the key of the TMA unit's descriptor cache — is the same in every launch
+//    (a __grid_constant__ kernel parameter lives at a new address per launch: measured 4 % slower in the step loop).  A tile is a strided
 //    1024 x 32-byte column block: four `cp.async.bulk.tensor.3d` box loads (8 floats x 256 rows) bring it into
 //    shared memory behind one mbarrier, and four tensor stores write the result back — the per-thread strided
 //    ld.global / st.global of the classic kernel (32 + 32 LSU instructions per thread, the floor of its ablation) are
@@ -53,9 +55,10 @@ struct FreqTmaCfg {
     static constexpr int LP_ENTRIES = 32 * Q2 * C;                  // operator entries per tile
 };
 
-template <bool LOCKSTEP>
+template <bool LOCKSTEP, bool STORE_TMA>
 __global__ void __launch_bounds__(512, 1)
-k_freq_tma(const __grid_constant__ CUtensorMap wmap, const float2* __restrict__ LP, const float2* __restrict__ tw,
+k_freq_tma(const CUtensorMap* __restrict__ wmap_ptr, float2* __restrict__ W, const float2* __restrict__ LP,
+           const float2* __restrict__ tw,
            int N1, int NP, const long long* __restrict__ converged_step, long long step_id,
            const long long* __restrict__ need_flag, long long need_id) {
     using namespace fft;
@@ -93,7 +96,7 @@ k_freq_tma(const __grid_constant__ CUtensorMap wmap, const float2* __restrict__ 
         mbar_init(lbar + 1, 1);
         mbar_fence_init();
         if (has_tile) {
-            tma_prefetch_desc(&wmap);
+            tma_prefetch_desc(wmap_ptr);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 mbar_expect_tx(lbar + j, Cfg::LP_CHUNK_BYTES);
@@ -122,7 +125,7 @@ k_freq_tma(const __grid_constant__ CUtensorMap wmap, const float2* __restrict__ 
         mbar_expect_tx(dbar, Cfg::TILE_BYTES);
 #pragma unroll
         for (int j = 0; j < Cfg::ROWS / Cfg::BOX_ROWS; ++j)
-            tma_load_3d(tile_buf + j * (Cfg::BOX_ROWS * C * 8), &wmap, 2 * tile * C, j * Cfg::BOX_ROWS, pol, dbar);
+            tma_load_3d(tile_buf + j * (Cfg::BOX_ROWS * C * 8), wmap_ptr, 2 * tile * C, j * Cfg::BOX_ROWS, pol, dbar);
     }
     mbar_wait(dbar, 0);
     float2 v[32];
@@ -153,18 +156,27 @@ k_freq_tma(const __grid_constant__ CUtensorMap wmap, const float2* __restrict__ 
 
     coop_fft_inverse<Q2, C, C, true, false>(v, xr, nullptr, tws, tws_lo, q, c, gsync);
 
-    // ---- tile out: stage in the landing layout, four tensor stores ------------------------------------------------------
-    gsync();  // last exchange reads done before the buffer is overwritten
+    // ---- tile out ------------------------------------------------------------------------------------------------------
+    if constexpr (STORE_TMA) {
+        // stage in the landing layout, four tensor stores
+        gsync();  // last exchange reads done before the buffer is overwritten
 #pragma unroll
-    for (int a = 0; a < 32; ++a) tile2[(Q2 * a + q) * C + c] = v[a];
-    fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy engine
-    gsync();
-    if (tg == 0) {
+        for (int a = 0; a < 32; ++a) tile2[(Q2 * a + q) * C + c] = v[a];
+        fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy engine
+        gsync();
+        if (tg == 0) {
 #pragma unroll
-        for (int j = 0; j < Cfg::ROWS / Cfg::BOX_ROWS; ++j)
-            tma_store_3d(&wmap, 2 * tile * C, j * Cfg::BOX_ROWS, pol, tile_buf + j * (Cfg::BOX_ROWS * C * 8));
-        tma_commit_group();
-        tma_wait_group_read0();  // shared memory may be released once the engine has read it
+            for (int j = 0; j < Cfg::ROWS / Cfg::BOX_ROWS; ++j)
+                tma_store_3d(wmap_ptr, 2 * tile * C, j * Cfg::BOX_ROWS, pol, tile_buf + j * (Cfg::BOX_ROWS * C * 8));
+            tma_commit_group();
+            tma_wait_group_read0();  // shared memory may be released once the engine has read it
+        }
+    } else {
+        // per-thread streaming stores (one 32-byte sector per 4 lanes), issued as each thread finishes its transform:
+        // the write traffic overlaps the other groups' arithmetic instead of arriving in one burst at the end
+        float2* base = W + ((int64_t)pol * (32 * Q2)) * N1 + tile * C + c;
+#pragma unroll
+        for (int a = 0; a < 32; ++a) st_stream(base + (int64_t)(Q2 * a + q) * N1, v[a]);
     }
 }
 

@@ -53,7 +53,7 @@ struct TimeArgs {
     FinalizeExt ext;      // TM_ITER: host mailbox + convergence flag (ext.mail == nullptr: unused)
     const long long* need_flag;  // speculative launch across a step boundary: run only if *need_flag == need_id
     long long need_id;
-    int kernel_choice;    // host side only: 0 per-mode default, 1 bulk-copy-fed kernel, 2 one-wave kernel (launch_time)
+    int kernel_choice;    // host side only: 1 selects the bulk-copy-fed kernel where it exists (launch_time)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -266,19 +266,16 @@ k_time(const TimeArgs A) {
 // LP is stored in consumption order: LP[((tile*32 + slot)*Q2 + q)*C + c], see k_tab_linop_perm.
 // ------------------------------------------------------------------------------------------
 // Shared memory of one k_freq CTA: the (half-footprint) exchange array, the twiddle table(s) and the tile's
-// whole operator slice, which is fetched by cp.async BEFORE the kernel waits for its predecessor.
+// whole operator slice, which the TMA engine fetches (cp.async.bulk) BEFORE the kernel waits for its predecessor.
 template <int Q2, int C>
 struct FreqCfg {
     static constexpr int STR = Q2 * C + C;
     static constexpr int TW_HALF = (Q2 == 32 ? 1 : 2) * 32 * Q2;  // a 32 x 32 table is symmetric: one copy
     static constexpr int TW_ENTRIES = (fft::kDS ? 2 : 1) * TW_HALF;   // hi parts, then lo parts
     static constexpr int LP_ENTRIES = 32 * Q2 * C;
-    static constexpr int SMEM_BYTES = 32 * STR * 4 + TW_ENTRIES * 8 + LP_ENTRIES * 8;
+    static constexpr int OFF_BAR = 32 * STR * 4 + TW_ENTRIES * 8 + LP_ENTRIES * 8;  // one mbarrier (operator slice landed)
+    static constexpr int SMEM_BYTES = OFF_BAR + 16;
 };
-__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-}
 template <int Q2, int C>
 __global__ void __launch_bounds__(Q2* C, (Q2 * C <= 256) ? 2 : 1)
 k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __restrict__ tw, int N1,
@@ -300,12 +297,20 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
     auto bsync = [] { __syncthreads(); };
 
     // Neither the operator table nor the twiddle table depends on the preceding kernel: fetch them now, so that
-    // the copies overlap the predecessor's tail (programmatic dependent launch) and this kernel's own W loads.
-    {
+    // the copies overlap the predecessor's tail (programmatic dependent launch) and this kernel's own W loads.  The
+    // tile's operator slice is one contiguous block (consumption order): ONE bulk copy by the TMA engine (cp.async.bulk,
+    // completion on an mbarrier) instead of 16 cp.async per thread.
+    uint64_t* lp_bar = reinterpret_cast<uint64_t*>(smem_raw + Cfg::OFF_BAR);
+    if (tid == 0) {
+        mbar_init(lp_bar, 1);
+        mbar_fence_init();
+        constexpr unsigned kChunk = 32768;  // keep every copy well inside the per-instruction size limit
+        mbar_expect_tx(lp_bar, Cfg::LP_ENTRIES * 8);
         const char* src = reinterpret_cast<const char*>(LP + (int64_t)tile * Cfg::LP_ENTRIES);
-        char* dst = reinterpret_cast<char*>(lps);
-        for (int i = tid; i < Cfg::LP_ENTRIES * 8 / 16; i += NT) cp_async16_cg(dst + i * 16, src + i * 16);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (unsigned off = 0; off < (unsigned)Cfg::LP_ENTRIES * 8; off += kChunk) {
+            const unsigned nb = min(kChunk, (unsigned)Cfg::LP_ENTRIES * 8 - off);
+            bulk_g2s(reinterpret_cast<char*>(lps) + off, src + off, nb, lp_bar);
+        }
     }
     // global table: hi, hi transposed, lo, lo transposed (32*Q2 entries each)
     for (int i = tid; i < Cfg::TW_HALF; i += NT) {
@@ -320,14 +325,15 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
     pdl_launch_dependents();
     if ((converged_step && *reinterpret_cast<const volatile long long*>(converged_step) == step_id) ||
         (need_flag && *reinterpret_cast<const volatile long long*>(need_flag) != need_id)) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();          // barrier initialisation visible
+        mbar_wait(lp_bar, 0);     // the bulk copy must land before the shared memory goes away
         return;
     }
     float2 v[32];
 #pragma unroll
     for (int a = 0; a < 32; ++a) v[a] = ld_stream(base + (int64_t)(Q2 * a + q) * N1);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();  // twiddle table and operator slice staged
+    __syncthreads();  // twiddle table staged, barrier initialisation visible
+    mbar_wait(lp_bar, 0);  // operator slice landed
     coop_fft_forward<Q2, C, C, true, false>(v, xr, nullptr, tws, tws_lo, q, c, bsync);
 #pragma unroll
     for (int s = 0; s < 32; ++s) v[s] = cmul(v[s], lps[s * NT + tid]);

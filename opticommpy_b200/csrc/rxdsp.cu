@@ -550,7 +550,7 @@ extern "C" int ocb_mimo_eq_run(const void* x, const void* ref, void* H, void* Hw
 // =============================================================================================
 namespace {
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_bps(const double2* __restrict__ X, int64_t L, const double2* __restrict__ cs, int M, int B, int Nh, int TS,
       int32_t* __restrict__ idx_out, double* __restrict__ ph_out) {
     extern __shared__ double sm[];
@@ -571,7 +571,8 @@ k_bps(const double2* __restrict__ X, int64_t L, const double2* __restrict__ cs, 
     for (int c = threadIdx.x; c < M; c += blockDim.x) csm[c] = cs[c];
     __syncthreads();
 
-    // phase A: dmin[b][j] for symbol k0 - Nh + j  (zero-padded outside [0, L): :203-206)
+    // phase A: dmin[b][j] for symbol k0 - Nh + j  (zero-padded outside [0, L): :203-206).  The M distances of an item are
+    // independent (the minimum is exact in any order): four running minima break the dependent fmin chain.
     for (int i = threadIdx.x; i < B * W; i += blockDim.x) {
         const int j = i % W, b = i / W;
         const int64_t k = k0 - Nh + j;
@@ -579,30 +580,73 @@ k_bps(const double2* __restrict__ X, int64_t L, const double2* __restrict__ cs, 
         if (k >= 0 && k < L) v = X[k * nModes + mode];
         const double2 r = rot[b];
         const double zr = v.x * r.x - v.y * r.y, zi = v.x * r.y + v.y * r.x;
-        double best = 1.0e300;
-        for (int c = 0; c < M; ++c) {
-            const double dr = zr - csm[c].x, di = zi - csm[c].y;
-            const double dd = dr * dr + di * di;  // :216
-            best = fmin(best, dd);                // :217
+        double m0 = 1.0e300, m1 = 1.0e300, m2 = 1.0e300, m3 = 1.0e300;
+        int c = 0;
+        for (; c + 4 <= M; c += 4) {
+            const double2 c0 = csm[c], c1 = csm[c + 1], c2 = csm[c + 2], c3 = csm[c + 3];
+            const double a0 = zr - c0.x, b0 = zi - c0.y, a1 = zr - c1.x, b1 = zi - c1.y;
+            const double a2 = zr - c2.x, b2 = zi - c2.y, a3 = zr - c3.x, b3 = zi - c3.y;
+            m0 = fmin(m0, a0 * a0 + b0 * b0);  // :216-217 (same expression per point: dr*dr + di*di)
+            m1 = fmin(m1, a1 * a1 + b1 * b1);
+            m2 = fmin(m2, a2 * a2 + b2 * b2);
+            m3 = fmin(m3, a3 * a3 + b3 * b3);
         }
-        dmin[(size_t)b * W + j] = best;
+        for (; c < M; ++c) {
+            const double dr = zr - csm[c].x, di = zi - csm[c].y;
+            m0 = fmin(m0, dr * dr + di * di);
+        }
+        dmin[(size_t)b * W + j] = fmin(fmin(m0, m1), fmin(m2, m3));
     }
     __syncthreads();
 
-    // phase B: window sums + argmin over b  (:218-221)
-    for (int j = threadIdx.x; j < TS; j += blockDim.x) {
-        const int64_t k = k0 + j;
-        if (k >= L) continue;
-        double best = 1.0e300;
-        int bi = 0;
-        for (int b = 0; b < B; ++b) {
+    // phase B: window sums + argmin over b  (:218-221).  Thread (h, j) handles the test phases b = h, h + NH, ... of
+    // symbol j; every window sum runs over t = 0 .. 2 Nh in that order (the summation order is part of the bit-exact
+    // contract), four sums at a time so that their dependent additions overlap.
+    const int NH = blockDim.x / TS;       // threads per symbol (host guarantees blockDim.x = NH * TS)
+    const int j = threadIdx.x % TS, h = threadIdx.x / TS;
+    const int per = (B + NH - 1) / NH;    // contiguous b range of this thread: [h*per, min(B, (h+1)*per))
+    double best = 1.0e300;
+    int bi = 0x7fffffff;
+    {
+        const int b_lo = h * per, b_hi = min(B, (h + 1) * per);
+        int b = b_lo;
+        for (; b + 4 <= b_hi; b += 4) {
+            const double* r0 = dmin + (size_t)b * W + j;
+            const double *r1 = r0 + W, *r2 = r1 + W, *r3 = r2 + W;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int t = 0; t <= 2 * Nh; ++t) { s0 += r0[t]; s1 += r1[t]; s2 += r2[t]; s3 += r3[t]; }
+            if (s0 < best) { best = s0; bi = b; }
+            if (s1 < best) { best = s1; bi = b + 1; }
+            if (s2 < best) { best = s2; bi = b + 2; }
+            if (s3 < best) { best = s3; bi = b + 3; }
+        }
+        for (; b < b_hi; ++b) {
             const double* row = dmin + (size_t)b * W + j;
             double s = 0.0;
             for (int t = 0; t <= 2 * Nh; ++t) s += row[t];
             if (s < best) { best = s; bi = b; }
         }
-        idx_out[k * nModes + mode] = bi;
-        ph_out[k * nModes + mode] = ((double)bi * (M_PI / 2.0)) / (double)B;
+    }
+    if (NH > 1) {
+        __syncthreads();  // dmin has been read by everyone: reuse its head as the hand-over buffer
+        double* hb = sm;                            // [NH][TS] best sums
+        int* hi = (int*)(sm + (size_t)NH * TS);     // [NH][TS] their indices
+        hb[h * TS + j] = best;
+        hi[h * TS + j] = bi;
+        __syncthreads();
+        if (h == 0) {
+            for (int q = 1; q < NH; ++q) {          // ascending b ranges: a later range wins only with a strictly smaller sum
+                const double ob = hb[q * TS + j];
+                if (ob < best) { best = ob; bi = hi[q * TS + j]; }
+            }
+        }
+    }
+    if (h == 0) {
+        const int64_t k = k0 + j;
+        if (k < L) {
+            idx_out[k * nModes + mode] = bi;
+            ph_out[k * nModes + mode] = ((double)bi * (M_PI / 2.0)) / (double)B;
+        }
     }
 }
 
@@ -614,14 +658,18 @@ extern "C" int ocb_bps_run(const void* x, int64_t L, int nModes, const void* con
     OCB_REQUIRE(L > 0 && nModes > 0 && M > 0 && B > 0 && Nhalf >= 0, "bps_run: bad sizes");
     OCB_REQUIRE(nModes <= 65535, "bps_run: too many modes");
     cudaStream_t st = (cudaStream_t)stream;
-    int TS = 256;
+    // Tile of TS symbols per CTA (+ 2*Nhalf halo columns); 512 threads = NH threads per symbol in the window-sum phase.
+    // TS = 128: 64 x 152 x 8 B = 78 KB at B = 64, N = 25 -> two CTAs (32 warps) per SM, 19 % halo recomputation.
+    int TS = 128;
     auto smem_for = [&](int ts) { return (size_t)B * (ts + 2 * Nhalf) * 8 + (size_t)(B + M) * 16; };
-    while (TS > 16 && smem_for(TS) > 200 * 1024) TS /= 2;
-    const size_t smem = smem_for(TS);
+    while (TS > 16 && smem_for(TS) > 100 * 1024) TS /= 2;
+    const int threads = 512, NH = threads / TS;
+    size_t smem = smem_for(TS);
+    if (smem < (size_t)NH * TS * 12 + 16) smem = (size_t)NH * TS * 12 + 16;  // hand-over buffer of the window-sum phase
     OCB_REQUIRE(smem <= 227 * 1024, "bps_run: B*(window) does not fit in shared memory");
     OCB_CUDA(cudaFuncSetAttribute(k_bps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((L + TS - 1) / TS), (unsigned)nModes);
-    OCB_LAUNCH(k_bps, grid, 256, smem, st, (const double2*)x, L, (const double2*)constSymb, M, B, Nhalf, TS,
+    OCB_LAUNCH(k_bps, grid, threads, smem, st, (const double2*)x, L, (const double2*)constSymb, M, B, Nhalf, TS,
                (int32_t*)idx_out, (double*)phase_out);
     return 0;
 }

@@ -70,11 +70,13 @@ struct ocb_ssfm_plan {
     float2 *tw1 = nullptr, *tw2 = nullptr, *tabV = nullptr, *tabU = nullptr;
     float2 *Cb = nullptr, *Nb = nullptr;  // third rotating field buffer, engine-layout noise copy
     // tuning / A-B knobs, read from the environment when the plan is created (fused_engine.inl)
-    int knob_time_kernel = 0;       // OCB_TIME_KERNEL: 0 per-mode default, 1 "bulk", 2 "plain"
-    bool knob_freq_tma = true;      // OCB_FREQ_TMA=0: classic k_freq instead of the TMA-fed one
+    int knob_time_kernel = 0;       // OCB_TIME_KERNEL: 0 default (one-wave kernel), 1 "bulk", 2 "plain" (= default)
+    bool knob_freq_tma = false;     // OCB_FREQ_TMA=1: tensor-map (TMA) tile loads / stores, k_freq_tma, instead of k_freq
     bool knob_freq_lockstep = false;  // OCB_FREQ_LOCKSTEP=1: CTA-wide instead of per-group barriers in k_freq_tma
+    bool knob_freq_tma_store = true;  // OCB_FREQ_TMA_STORE=0: tensor loads, per-thread streaming stores
     int knob_freq_c = 16;           // OCB_FREQ_C=8: tile width of the classic k_freq at N2 = 1024
     CUtensorMap wmap;      // W buffer as float32 [rows][N2][2*N1] for the TMA-fed frequency pass (N2 = 1024)
+    CUtensorMap* wmap_dev = nullptr;  // its copy in the workspace (device memory, 64-byte aligned)
     bool wmap_ok = false;
     // table cache keys
     double t1_h = NAN, t1_a = NAN, t1_b = NAN, t1_scale = NAN;
@@ -150,6 +152,7 @@ static int make_w_tensor_map(ocb_ssfm_plan* p) {
         char b[128]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d)", (int)r);
         return fail(b, __FILE__, __LINE__);
     }
+    OCB_CUDA(cudaMemcpy(p->wmap_dev, &p->wmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     p->wmap_ok = true;
     return 0;
 }
@@ -170,8 +173,9 @@ extern "C" int ocb_ssfm_plan_create(int64_t N, int rows, ocb_ssfm_plan** out) {
     {
         const char* v = getenv("OCB_TIME_KERNEL");
         p->knob_time_kernel = (v && !strcmp(v, "bulk")) ? 1 : (v && !strcmp(v, "plain")) ? 2 : 0;
-        p->knob_freq_tma = !(getenv("OCB_FREQ_TMA") && atoi(getenv("OCB_FREQ_TMA")) == 0);
+        p->knob_freq_tma = getenv("OCB_FREQ_TMA") && atoi(getenv("OCB_FREQ_TMA")) != 0;
         p->knob_freq_lockstep = getenv("OCB_FREQ_LOCKSTEP") && atoi(getenv("OCB_FREQ_LOCKSTEP")) != 0;
+        p->knob_freq_tma_store = !(getenv("OCB_FREQ_TMA_STORE") && atoi(getenv("OCB_FREQ_TMA_STORE")) == 0);
         p->knob_freq_c = (getenv("OCB_FREQ_C") && atoi(getenv("OCB_FREQ_C")) == 8) ? 8 : 16;
     }
     if (cufftCreate(&p->fft) != CUFFT_SUCCESS) { delete p; return fail("cufftCreate failed", __FILE__, __LINE__); }
@@ -205,6 +209,7 @@ extern "C" int64_t ocb_ssfm_plan_workspace_bytes(const ocb_ssfm_plan* p) {
     b += align_up(((int64_t)(p->rows + 1) / 2) * p->N * sizeof(float), 256);  // Pch
     b += align_up((int64_t)p->max_blocks * 3 * sizeof(double), 256);  // partials
     b += 256;                                                         // sums + ticket
+    b += 256;                                                         // tensor map of the W buffer
     b += align_up((int64_t)p->fft_work, 256);
     b += fused_table_bytes(p);
     return b;
@@ -226,6 +231,7 @@ extern "C" int ocb_ssfm_plan_bind_workspace(ocb_ssfm_plan* p, void* dev_ptr, int
     p->Pch = (float*)c; c += align_up(((int64_t)(p->rows + 1) / 2) * p->N * sizeof(float), 256);
     p->partials = (double*)c; c += align_up((int64_t)p->max_blocks * 3 * sizeof(double), 256);
     p->sums = (double*)c; p->ticket = (unsigned*)(c + 64); p->conv_flag = (long long*)(c + 128); p->final_flag = (long long*)(c + 192); c += 256;
+    p->wmap_dev = (CUtensorMap*)c; c += 256;
     p->fft_area = c; c += align_up((int64_t)p->fft_work, 256);
     if (p->fft_work > 0) OCB_CUFFT(cufftSetWorkArea(p->fft, p->fft_area));
     if (p->fused_ok) {

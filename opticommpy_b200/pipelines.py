@@ -72,7 +72,7 @@ def pnorm_rows_device(rows):
     torch = _cabi.require_cuda()
     lib = _cabi.lib()
     st = _vp(_cabi.stream_ptr(torch))
-    n = rows.numel()
+    n = rows.numel() // (1 if rows.is_complex() else 2)   # complex elements (float-pair tensors carry a trailing 2)
     d128 = torch.empty((n, 2), dtype=torch.float64, device="cuda")
     _cabi.check(lib.ocb_cast_complex(_ptr(rows), _cabi.OCB_C64, _ptr(d128), _cabi.OCB_C128, n, st), "ocb_cast_complex")
     d_ws = torch.empty(4096 + 32, dtype=torch.float64, device="cuda")

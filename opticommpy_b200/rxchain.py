@@ -59,10 +59,9 @@ def rxChain(sigIn, paramEDC, paramEq, paramCPR, symbRef=None, returnAll=False, t
     # ---- upload once (raw dtype), planar rows for the EDC --------------------------------------------------------
     mark(0)
     host = s.sig
-    pinned = torch.empty(host.shape + (2,), dtype=torch.float32 if host.dtype == np.complex64 else torch.float64,
-                         pin_memory=True)
-    pinned.numpy()[...] = host.view(np.float32 if host.dtype == np.complex64 else np.float64).reshape(host.shape + (2,))
-    d_raw = pinned.to("cuda", non_blocking=True)
+    # one host -> device copy of the raw samples (pageable memory is fine for a single transfer; allocating a pinned
+    # staging buffer per call costs far more than it saves)
+    d_raw = torch.from_numpy(host.view(np.float32 if host.dtype == np.complex64 else np.float64).reshape(host.shape + (2,))).to("cuda")
     d_rows = torch.empty((nM, Nsig, 2), dtype=torch.float32, device="cuda")
     _cabi.check(lib.ocb_pack_fields(_ptr(d_raw), _engine.dtype_tag(host.dtype), Nsig, nM, 0, _ptr(d_rows), st), "ocb_pack_fields")
     mark(1)

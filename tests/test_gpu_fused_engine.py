@@ -183,16 +183,16 @@ def test_full_size_fused_vs_cufft_engine(api):
 
 
 def test_kernel_variants_are_bit_identical(api):
-    """Data-path and launch options that must not change a single bit: the TMA-fed frequency pass vs the classic one,
-    per-group vs CTA-wide barriers in it, the bulk-copy-fed vs the one-wave time pass for every mode, programmatic
-    dependent launch off and the step prediction off."""
+    """Data-path and launch options that must not change a single bit: the tensor-map (TMA) frequency pass vs the default
+    one (with tensor or per-thread stores, per-group or CTA-wide barriers), 64-byte tiles, the persistent bulk-copy-fed
+    time pass vs the one-wave one, programmatic dependent launch off and the step prediction off."""
     import os
     x = field(11, 1 << 20, 2, 6e-3)
     kw = dict(Fs=512e9, Ltotal=1.6, Lspan=0.8, hz=0.08, amp="ideal", nlprMethod=False, saveSpanN=[], prgsBar=False)
     api.eng.set_default_engine("fused")
     ref = api.manakovSSF(x, Bag(**kw))
-    for var in ({"OCB_FREQ_TMA": "0"}, {"OCB_FREQ_TMA": "0", "OCB_FREQ_C": "8"}, {"OCB_FREQ_LOCKSTEP": "1"},
-                {"OCB_TIME_KERNEL": "plain"}, {"OCB_TIME_KERNEL": "bulk"}, {"OCB_PDL": "0"}, {"OCB_PREDICT": "0"}):
+    for var in ({"OCB_FREQ_TMA": "1"}, {"OCB_FREQ_TMA": "1", "OCB_FREQ_TMA_STORE": "0"}, {"OCB_FREQ_TMA": "1", "OCB_FREQ_LOCKSTEP": "1"},
+                {"OCB_FREQ_C": "8"}, {"OCB_TIME_KERNEL": "bulk"}, {"OCB_PDL": "0"}, {"OCB_PREDICT": "0"}):
         os.environ.update(var)
         try:
             api.eng.clear_plans()  # the data-path knobs are read when a plan is created
