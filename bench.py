@@ -115,13 +115,17 @@ def measured_hbm_peak():
 
 
 def ncu_traffic(engine):
-    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f)
-        return t["k_time_iter_bytes"] if engine == "fused" else t["k_manakov_nl_iter_bytes"]
-    except Exception:
-        return None
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture, with its provenance (the
+    figure is a profile constant, not measured in this run)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            v = t["k_time_iter_bytes"] if engine == "fused" else t["k_manakov_nl_iter_bytes"]
+            return v, {"file": f"profiles/{name}", "source": t.get("source"), "captured": t.get("captured")}
+        except Exception:
+            continue
+    return None, None
 
 
 def cpu_oracle_rate(n_steps, n=N_SAMPLES, seed=0):
@@ -476,7 +480,8 @@ def main():
                                                     if plan.engine == "fused" else
                                                     "k_manakov_nl<false,2> (convergence sums + Kerr phase/rotation)"),
                          "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(plan.engine),
+                         "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(plan.engine)[0],
+                         "traffic_source": ncu_traffic(plan.engine)[1],
                          "launches_timed": 200 if pass_us else int(nl_n), "avg_us": kern_us,
                          "how": ("200 back-to-back launches on the plan's L2-resident buffers, one CUDA-event pair on the launch stream"
                                  if pass_us else "CUDA-event pair around every launch of one extra span"),
