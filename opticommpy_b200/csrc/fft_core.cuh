@@ -21,15 +21,21 @@ __device__ __forceinline__ void static_for(F&& f) {
     }
 }
 
-// Double-single twiddles (OCB_DS, default on).  Every twiddle factor w is kept as an unevaluated sum hi + lo of two
-// floats (lo = float(w - hi), about 2^-24 |w|) and a product x*w is evaluated as x*hi + x*lo.  The FIXED rounding
-// error of a float twiddle (~3e-8 relative) acts on nearly the same field in every split-step, so it accumulates
-// linearly with the step count (measured 2.2e-7 per step in round 1); with the lo term the fixed error drops to
-// ~1e-15 and what is left is the data-dependent rounding of the float arithmetic, which grows like a random walk.
-#ifndef OCB_DS
-#define OCB_DS 1
+// Twiddle precision (OCB_TW_MODE).  The FIXED rounding error of a float twiddle (~3e-8 relative) acts on nearly the same
+// field in every split-step, so it accumulates linearly with the step count (measured 2.6e-7 per step with plain float
+// twiddles, tools/drift_experiment.py).
+//   0  plain float twiddles (round 1)
+//   1  double-single (default): every twiddle is an unevaluated sum hi + lo of two floats (lo = float(w - hi), about
+//      2^-24 |w|) and a product x*w is evaluated as x*hi + x*lo inside ONE fused chain, so that the lo term takes part in
+//      the rounding of the result: +4 FMA per complex multiply.  The fixed error drops to ~1e-15 and what is left is the
+//      rounding of the linear-operator table plus the data-dependent rounding of the float arithmetic: 3.9e-8 per step.
+// (A cheaper variant — compensate only the modulus error, z + eps*z after the float product — was measured and does not
+// work: eps*z is below half an ulp of z, so the separate correction never changes the rounded result; 1.7e-7 per step.)
+#ifndef OCB_TW_MODE
+#define OCB_TW_MODE 1
 #endif
-constexpr bool kDS = (OCB_DS != 0);
+constexpr bool kDS = (OCB_TW_MODE == 1);
+constexpr bool kLO = kDS;                   // a second table entry (the lo part) per twiddle exists
 
 // cos(2 pi k / 32), k = 0..8, to double precision
 __host__ __device__ constexpr double cos32_qd(int k) {
@@ -97,7 +103,7 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
 #endif
 }
 
-// a * (h + l) and a * conj(h + l) for a double-single factor (l is ignored when OCB_DS = 0)
+// a * (h + l) and a * conj(h + l) for a double-single factor (l is ignored in mode 0)
 __device__ __forceinline__ float2 cmul_ds(float2 a, float2 h, float2 l) {
     if constexpr (kDS) {
         return make_float2(fmaf(a.x, h.x, fmaf(-a.y, h.y, fmaf(a.x, l.x, -a.y * l.y))),
@@ -114,6 +120,16 @@ __device__ __forceinline__ float2 cmul_conj_ds(float2 a, float2 h, float2 l) {
         return cmul_conj(a, h);
     }
 }
+// inter-pass twiddle x * V * U (or x * conj(V U)) from its two table factors: in double-single mode the factors are
+// applied one after the other (a float product V*U would carry its own fixed rounding error)
+template <bool CONJ>
+__device__ __forceinline__ float2 cmul_vu(float2 x, float2 vh, float2 vl, float2 uh, float2 ul) {
+    if constexpr (kDS) {
+        return CONJ ? cmul_conj_ds(cmul_conj_ds(x, vh, vl), uh, ul) : cmul_ds(cmul_ds(x, vh, vl), uh, ul);
+    } else {
+        return CONJ ? cmul_conj(x, cmul(vh, uh)) : cmul(x, cmul(vh, uh));
+    }
+}
 
 // t * exp(DIR * 2 pi i * J / LEN), J and LEN compile-time (trivial factors cost no multiply)
 template <int LEN, int J, int DIR>
@@ -127,7 +143,7 @@ __device__ __forceinline__ float2 twiddle_mul(float2 t) {
         return make_float2(-t.x, -t.y);
     } else if constexpr (K == 24) {
         return DIR > 0 ? make_float2(t.y, -t.x) : make_float2(-t.y, t.x);
-    } else if constexpr (kDS && (K == 4 || K == 12)) {
+    } else if constexpr (kLO && (K == 4 || K == 12)) {
         // exp(DIR i pi/4) = r (1 + DIR i), exp(DIR 3 i pi/4) = r (-1 + DIR i), r = sqrt(1/2) = rh + rl
         constexpr float rh = hi_part(cos32d(4)), rl = lo_part(cos32d(4));
         constexpr float d = (DIR > 0 ? 1.f : -1.f);
@@ -203,7 +219,7 @@ struct Coop {
 
 // HALF = true: the exchange runs in two rounds (real parts, then imaginary parts) through ONE planar array
 // (xr; xi unused), which halves the shared-memory footprint at the price of two more barriers per transform.
-// tw_lo: the lo parts of the table, same layout (read only when OCB_DS = 1)
+// tw_lo: the second table (lo parts or modulus corrections), same layout (read only when OCB_TW_MODE != 0)
 template <int Q, int CP, int PAD, bool HALF = false, bool PK = true, typename SyncF>
 __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi, const float2* __restrict__ tw,
                                                  const float2* __restrict__ tw_lo, int q, int c, SyncF&& sync) {
@@ -213,7 +229,7 @@ __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi
         static_for<0, 32>([&](auto kk) {
             constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
             float2 z = v[SLOT];
-            if constexpr (KA != 0) z = cmul_ds(z, tw[KA * Q + q], kDS ? tw_lo[KA * Q + q] : float2{});
+            if constexpr (KA != 0) z = cmul_ds(z, tw[KA * Q + q], kLO ? tw_lo[KA * Q + q] : float2{});
             xr[KA * STR + q * CP + c] = z.x;
             xi[KA * STR + q * CP + c] = z.y;
         });
@@ -230,7 +246,7 @@ __device__ __forceinline__ void coop_fft_forward(float2* v, float* xr, float* xi
     } else {
         static_for<0, 32>([&](auto kk) {
             constexpr int KA = decltype(kk)::value, SLOT = brev<32>(KA);
-            if constexpr (KA != 0) v[SLOT] = cmul_ds(v[SLOT], tw[KA * Q + q], kDS ? tw_lo[KA * Q + q] : float2{});
+            if constexpr (KA != 0) v[SLOT] = cmul_ds(v[SLOT], tw[KA * Q + q], kLO ? tw_lo[KA * Q + q] : float2{});
             xr[KA * STR + q * CP + c] = v[SLOT].x;
         });
         sync();
@@ -271,7 +287,7 @@ __device__ __forceinline__ void coop_fft_inverse(float2* v, float* xr, float* xi
         static_for<0, Q>([&](auto jj) {
             constexpr int J = decltype(jj)::value;  // q'
             // transposed copy of the table: entry [J][ka], so that lanes (ka) are contiguous
-            const float2 z = cmul_conj_ds(v[GI * Q + J], twt[J * 32 + ka], kDS ? twt_lo[J * 32 + ka] : float2{});  // conj twiddle
+            const float2 z = cmul_conj_ds(v[GI * Q + J], twt[J * 32 + ka], kLO ? twt_lo[J * 32 + ka] : float2{});  // conj twiddle
             v[GI * Q + J] = z;
             xr[ka * STR + J * CP + c] = z.x;
             if constexpr (!HALF) xi[ka * STR + J * CP + c] = z.y;

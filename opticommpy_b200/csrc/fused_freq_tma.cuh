@@ -46,7 +46,7 @@ struct FreqTmaCfg {
     static constexpr int LP_CHUNK_SLOTS = 8, LP_CHUNKS = 32 / LP_CHUNK_SLOTS;
     static constexpr int LP_CHUNK_BYTES = LP_CHUNK_SLOTS * NT * 8;  // 8 KB
     static constexpr int TW_HALF = 1024;
-    static constexpr int TW_ENTRIES = (fft::kDS ? 2 : 1) * TW_HALF;
+    static constexpr int TW_ENTRIES = (fft::kLO ? 2 : 1) * TW_HALF;
     static constexpr int OFF_TW = 0;
     static constexpr int OFF_TILE = OFF_TW + TW_ENTRIES * 8;
     static constexpr int OFF_LP = OFF_TILE + GROUPS * TILE_BYTES;
@@ -106,7 +106,7 @@ k_freq_tma(const CUtensorMap* __restrict__ wmap_ptr, float2* __restrict__ W, con
     }
     for (int i = tid; i < Cfg::TW_HALF; i += 512) {
         tws[i] = __ldg(tw + i);
-        if constexpr (kDS) tws[Cfg::TW_HALF + i] = __ldg(tw + 64 * Q2 + i);
+        if constexpr (kLO) tws[Cfg::TW_HALF + i] = __ldg(tw + 64 * Q2 + i);
     }
     __syncthreads();
 

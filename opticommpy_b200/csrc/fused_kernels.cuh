@@ -86,18 +86,16 @@ k_time(const TimeArgs A) {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         wV[g] = __ldg(A.tabV + (int64_t)row * 32 + t * G + g);
-        wVl[g] = kDS ? __ldg(A.tabV + (int64_t)(A.N2 + row) * 32 + t * G + g) : float2{};
+        wVl[g] = kLO ? __ldg(A.tabV + (int64_t)(A.N2 + row) * 32 + t * G + g) : float2{};
     }
     const float2* Urow = A.tabU + (int64_t)row * Q1;
     const float2* Urow_lo = A.tabU + (int64_t)(A.N2 + row) * Q1;
     // inter-pass twiddle W_N^{n2 k1} = V[n2][ka] U[n2][kq], applied factor by factor
     auto twiddle_fwd = [&](float2 x, int gi, int kq) {
-        if constexpr (kDS) return cmul_ds(cmul_ds(x, wV[gi], wVl[gi]), __ldg(Urow + kq), __ldg(Urow_lo + kq));
-        else return cmul(x, cmul(wV[gi], __ldg(Urow + kq)));
+        return cmul_vu<false>(x, wV[gi], wVl[gi], __ldg(Urow + kq), kLO ? __ldg(Urow_lo + kq) : float2{});
     };
     auto twiddle_inv = [&](float2 x, int gi, int kq) {
-        if constexpr (kDS) return cmul_conj_ds(cmul_conj_ds(x, wV[gi], wVl[gi]), __ldg(Urow + kq), __ldg(Urow_lo + kq));
-        else return cmul_conj(x, cmul(wV[gi], __ldg(Urow + kq)));
+        return cmul_vu<true>(x, wV[gi], wVl[gi], __ldg(Urow + kq), kLO ? __ldg(Urow_lo + kq) : float2{});
     };
 
     // Secondary streams of the pointwise stage: start their HBM->L2 fetch now so that it overlaps the
@@ -271,7 +269,7 @@ template <int Q2, int C>
 struct FreqCfg {
     static constexpr int STR = Q2 * C + C;
     static constexpr int TW_HALF = (Q2 == 32 ? 1 : 2) * 32 * Q2;  // a 32 x 32 table is symmetric: one copy
-    static constexpr int TW_ENTRIES = (fft::kDS ? 2 : 1) * TW_HALF;   // hi parts, then lo parts
+    static constexpr int TW_ENTRIES = (fft::kLO ? 2 : 1) * TW_HALF;   // hi parts, then lo parts
     static constexpr int LP_ENTRIES = 32 * Q2 * C;
     static constexpr int OFF_BAR = 32 * STR * 4 + TW_ENTRIES * 8 + LP_ENTRIES * 8;  // one mbarrier (operator slice landed)
     static constexpr int SMEM_BYTES = OFF_BAR + 16;
@@ -315,7 +313,7 @@ k_freq(float2* __restrict__ W, const float2* __restrict__ LP, const float2* __re
     // global table: hi, hi transposed, lo, lo transposed (32*Q2 entries each)
     for (int i = tid; i < Cfg::TW_HALF; i += NT) {
         tws[i] = __ldg(tw + i);
-        if constexpr (kDS) tws[Cfg::TW_HALF + i] = __ldg(tw + 64 * Q2 + i);
+        if constexpr (kLO) tws[Cfg::TW_HALF + i] = __ldg(tw + 64 * Q2 + i);
     }
     const float2* twt = (Q2 == 32) ? tws : tws + 32 * Q2;
     const float2* tws_lo = tws + Cfg::TW_HALF;
@@ -364,6 +362,10 @@ __global__ void k_transpose(const float2* __restrict__ in, float2* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // Table builders (float64 math, rounded once to float32).
 // ------------------------------------------------------------------------------------------
+// second table entry of a twiddle whose exact value is (c, s) and whose float value is hi: the lo part (fft_core.cuh)
+__device__ __forceinline__ float2 second_entry(float2 hi, double c, double s) {
+    return make_float2((float)(c - (double)hi.x), (float)(s - (double)hi.y));
+}
 // tw[ka*Q + q] = exp(-2 pi i q ka / (32 Q)): hi parts, hi parts transposed [q*32 + ka], lo parts, lo parts transposed
 // (32*Q entries each; the lo parts are what float rounding dropped, see fft_core.cuh)
 __global__ void k_tab_tw(float2* tw, int Q) {
@@ -373,7 +375,7 @@ __global__ void k_tab_tw(float2* tw, int Q) {
     double s, c;
     sincospi(-2.0 * (double)(q * ka) / (double)(32 * Q), &s, &c);
     const float2 hi = make_float2((float)c, (float)s);
-    const float2 lo = make_float2((float)(c - (double)hi.x), (float)(s - (double)hi.y));
+    const float2 lo = second_entry(hi, c, s);
     tw[i] = hi;
     tw[32 * Q + q * 32 + ka] = hi;
     tw[64 * Q + i] = lo;
@@ -388,7 +390,7 @@ __global__ void k_tab_inter(float2* V, float2* U, int N2, int Q1, int64_t N) {
         sincospi(-2.0 * (double)((n2 * ka) % N) / (double)N, &s, &c);
         const float2 hi = make_float2((float)c, (float)s);
         V[i] = hi;
-        V[(int64_t)N2 * 32 + i] = make_float2((float)(c - (double)hi.x), (float)(s - (double)hi.y));
+        V[(int64_t)N2 * 32 + i] = second_entry(hi, c, s);
     }
     if (i < (int64_t)N2 * Q1) {
         const int64_t n2 = i / Q1, kq = i % Q1;
@@ -396,7 +398,7 @@ __global__ void k_tab_inter(float2* V, float2* U, int N2, int Q1, int64_t N) {
         sincospi(-2.0 * (double)((n2 * 32 * kq) % N) / (double)N, &s, &c);
         const float2 hi = make_float2((float)c, (float)s);
         U[i] = hi;
-        U[(int64_t)N2 * Q1 + i] = make_float2((float)(c - (double)hi.x), (float)(s - (double)hi.y));
+        U[(int64_t)N2 * Q1 + i] = second_entry(hi, c, s);
     }
 }
 __host__ __device__ inline int brev_rt(int v, int bits) {

@@ -29,7 +29,7 @@ namespace ocb {
 
 struct TimeBulkCfg {
     static constexpr int N1 = 1024, WARPS = 8;
-    static constexpr int TW_ENTRIES = (fft::kDS ? 2 : 1) * 1024;       // symmetric 32 x 32 table: hi (+ lo)
+    static constexpr int TW_ENTRIES = (fft::kLO ? 2 : 1) * 1024;       // symmetric 32 x 32 table: hi (+ lo)
     static constexpr int XBUF_FLOATS = 32 * 33;                        // half-footprint exchange, one plane
     static constexpr int ROW_BYTES = N1 * 8;
     static constexpr int OFF_TW = 0;
@@ -99,7 +99,7 @@ k_time_bulk(const TimeArgs A) {
     }
     for (int i = tid; i < 1024; i += 256) {
         tws[i] = __ldg(A.tw + i);
-        if constexpr (kDS) tws[1024 + i] = __ldg(A.tw + 64 * Q1 + i);
+        if constexpr (kLO) tws[1024 + i] = __ldg(A.tw + 64 * Q1 + i);
     }
     __syncthreads();  // table staged, barriers initialised
 
@@ -138,7 +138,7 @@ k_time_bulk(const TimeArgs A) {
         const int64_t base = (int64_t)pol * A.N + (int64_t)row * N1;
         const int next_unit = unit + unit_stride;
         const float2 wV = __ldg(A.tabV + (int64_t)row * 32 + t);
-        const float2 wVl = kDS ? __ldg(A.tabV + (int64_t)(A.N2 + row) * 32 + t) : float2{};
+        const float2 wVl = kLO ? __ldg(A.tabV + (int64_t)(A.N2 + row) * 32 + t) : float2{};
         const float2* Urow = A.tabU + (int64_t)row * Q1;
         const float2* Urow_lo = A.tabU + (int64_t)(A.N2 + row) * Q1;
         float2 v[32];
@@ -154,8 +154,7 @@ k_time_bulk(const TimeArgs A) {
             for (int s = 0; s < 32; ++s) v[s] = ld_stream(src + s * Q1 + t);
             static_for<0, Q1>([&](auto kk) {
                 constexpr int KQ = decltype(kk)::value, SLOT = brev<Q1>(KQ);
-                if constexpr (kDS) v[SLOT] = cmul_conj_ds(cmul_conj_ds(v[SLOT], wV, wVl), __ldg(Urow + KQ), __ldg(Urow_lo + KQ));
-                else v[SLOT] = cmul_conj(v[SLOT], cmul(wV, __ldg(Urow + KQ)));  // conj twiddle W_N^{-n2 k1}
+                v[SLOT] = cmul_vu<true>(v[SLOT], wV, wVl, __ldg(Urow + KQ), kLO ? __ldg(Urow_lo + KQ) : float2{});  // W_N^{-n2 k1}
             });
             coop_fft_inverse<Q1, 1, 1, true>(v, xr, nullptr, tws, tws_lo, t, 0, wsync);  // v[a'] = sample n1 = 32 a' + t
             phase_sync();  // exchange buffer free again; lockstep
@@ -242,10 +241,7 @@ k_time_bulk(const TimeArgs A) {
             float2* dst = A.out + base;
             static_for<0, Q1>([&](auto kk) {
                 constexpr int KQ = decltype(kk)::value, SLOT = brev<Q1>(KQ);
-                float2 o;
-                if constexpr (kDS) o = cmul_ds(cmul_ds(v[SLOT], wV, wVl), __ldg(Urow + KQ), __ldg(Urow_lo + KQ));
-                else o = cmul(v[SLOT], cmul(wV, __ldg(Urow + KQ)));
-                st_stream(dst + SLOT * Q1 + t, o);
+                st_stream(dst + SLOT * Q1 + t, cmul_vu<false>(v[SLOT], wV, wVl, __ldg(Urow + KQ), kLO ? __ldg(Urow_lo + KQ) : float2{}));
             });
         }
     }

@@ -1,7 +1,7 @@
 """Accumulated complex64 error of the fused engine against the CPU oracle as a function of the number of
 SSFM steps (N = 2^16, cfg2 fiber: Fs = 512 GSa/s, hz = 0.08 km, 11 x -2 dBm), plus the per-pass kernel times
-at N = 2^20.  `OCB_LIB=<path>` selects another build of the library (e.g. the OCB_DS=0 build made by
-`make -C opticommpy_b200/csrc nods`) for an A/B of the double-single twiddles.  Prints one JSON line."""
+at N = 2^20.  `OCB_LIB=<path>` selects another build of the library (e.g. an OCB_TW_MODE=0/1 build made by
+`make -C opticommpy_b200/csrc twmodes`) for an A/B of the double-single twiddles.  Prints one JSON line."""
 import ctypes as C
 import json
 import os
