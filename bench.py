@@ -343,6 +343,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, where exactly one JSON line belongs
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _cabi.lib()
     st = C.c_void_p(_cabi.stream_ptr(torch))
