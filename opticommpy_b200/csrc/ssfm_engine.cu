@@ -296,6 +296,9 @@ extern "C" int ocb_ssfm_plan_profile_read(ocb_ssfm_plan* p, double* out6) {
 
 extern "C" int ocb_ssfm_plan_destroy(ocb_ssfm_plan* p) {
     if (!p) return 0;
+    // lines of the operator tables that were marked persisting in L2 during fused runs go back to normal before the
+    // workspace can be freed by its owner
+    if (p->fused_ok && p->ws) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
     for (int k = 0; k < ocb_ssfm_plan::kProfKinds; ++k)
         for (auto& e : p->prof_ev[k]) cudaEventDestroy(e);
     if (p->fft_ok) cufftDestroy(p->fft);

@@ -103,3 +103,18 @@ def test_frontend_argument_errors():
         firFilter(np.ones(5000), x)   # filter longer than the signal: not supported on the GPU path
     with pytest.raises(ValueError):
         firFilter(np.ones(0), x)
+
+
+def test_bench_host_helpers():
+    """bench.py / bench_extras.py pieces that need no GPU: the static config shared by both arms, the WDM input generator
+    (reference transmitter when baseline/_ref or /root/reference is importable, else the synthetic stand-in) and the
+    provenance of the roofline traffic figure."""
+    import bench
+    import bench_extras as bx
+    assert bench.static_config(10, 1) == bench.static_config(10, 1) and "workload" in bench.static_config(10, 8)
+    v, src = bench.ncu_traffic("fused")
+    assert v and v > 1e7 and src["file"].startswith("profiles/") and src["captured"]
+    sig, symb, grid, pulse, source = bx.wdm_waveform(3, 8, 8, seed=1)
+    assert sig.shape == (256 * 8, 2) and symb.shape == (256, 2, 3) and len(grid) == 3 and len(pulse) == 1024
+    p_tot = np.mean(np.sum(np.abs(sig) ** 2, axis=1))
+    assert 0.5 * 3 * 10 ** (-0.2) * 1e-3 < p_tot < 2 * 3 * 10 ** (-0.2) * 1e-3     # 3 channels at -2 dBm
