@@ -194,11 +194,16 @@ def extra_rx_chain(torch, peak_gbs, nsym_log2=21, cpu_nsym_log2=15):
 
 
 # ---- cfg4: per-channel DBP, channels sharded --------------------------------------------------------------------------------
+def unit_workers():
+    """Units (channels, seeds) kept in flight per GPU by sharding.run_concurrent in the sharded extras (OCB_UNIT_WORKERS)."""
+    return max(1, int(os.environ.get("OCB_UNIT_WORKERS", "4")))
+
+
 def extra_cfg4_dbp(torch, dist, world, rank, spans=10, hz_dbp=0.8):
     import bench
     from opticommpy_b200.channels import manakov_rows_device
     from opticommpy_b200.pipelines import dbp_channel_device, upload_field
-    from opticommpy_b200.sharding import gather_device, shard_units
+    from opticommpy_b200.sharding import gather_device, run_concurrent, shard_units
     n_ch, sps, rs = 11, 16, 32e9
     fs = rs * sps
     sig, symb, grid, pulse, source = wdm_waveform(n_ch, 16, sps, seed=123)
@@ -208,14 +213,15 @@ def extra_cfg4_dbp(torch, dist, world, rank, spans=10, hz_dbp=0.8):
     prm = Bag(Fs=2 * rs, Ltotal=80 * spans, Lspan=80, hz=hz_dbp, alpha=0.2, D=16, gamma=1.3, Fc=193.1e12, amp="edfa", NF=4.5,
               maxIter=10, tol=1e-5, nlprMethod=False, maxNlinPhaseRot=2e-2, seed=None)
     mine = shard_units(n_ch, rank, world)
-    dbp_channel_device(rows, float(grid[n_ch // 2]), fs, pulse, sps, prm)  # warm-up (plans, tables)
+    nw = unit_workers()
+    unit = lambda k: dbp_channel_device(rows, float(grid[k]), fs, pulse, sps, prm)
+    run_concurrent(unit, [n_ch // 2] * nw, nw)  # warm-up (plans and tables of every worker stream)
     _sync(torch, dist, world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    local, steps = {}, 0
-    for k in mine:
-        local[k], st = dbp_channel_device(rows, float(grid[k]), fs, pulse, sps, prm)
-        steps += st["steps"]
+    done = run_concurrent(unit, mine, nw)  # up to nw channels in flight on this GPU, one stream + plan each
+    local = {k: v[0] for k, v in done.items()}
+    steps = sum(v[1]["steps"] for v in done.values())
     full = gather_device(local, n_ch)  # the path's only collective: 11 x (2, 2^17) complex64 fields over NVLink
     e1.record()
     _sync(torch, dist, world)
@@ -229,7 +235,7 @@ def extra_cfg4_dbp(torch, dist, world, rank, spans=10, hz_dbp=0.8):
     return {"workload": f"cfg4: 11-ch WDM after the cfg2 link ({spans} x 80 km), per channel: CW-LO coherent front end (down-shift) + matched filter + "
                         f"decimate 16->2 SpS + manakovDBP ({spans} spans, hz = {hz_dbp} km, N = 2^17), one channel per shard unit",
             "input": source, "value": n2 * float(tot_steps.item()) / (ms * 1e-3) / 1e6, "unit": "Msamples/s (DBP sample-steps)",
-            "seconds": ms * 1e-3, "channels": n_ch, "shard_sizes": sizes,
+            "seconds": ms * 1e-3, "channels": n_ch, "shard_sizes": sizes, "units_in_flight_per_gpu": nw,
             "balance_bound": n_ch / (max(sizes) * world), "dbp_steps_total": int(tot_steps.item()),
             "gathered": [int(v) for v in full[0].shape], "gather": "one all_gather of the device tensors (no host round trip)"}
 
@@ -241,7 +247,7 @@ def extra_cfg5_mc(torch, dist, world, rank, n_seeds=64, spans=3, hz=0.1):
     from opticommpy_b200.core import symbolSync
     from opticommpy_b200.pipelines import RxRecipe, ber_scalars_device, channel_frontend_device, rx_symbols_device, upload_field
     from opticommpy_b200.equalization import edc_rows_device
-    from opticommpy_b200.sharding import gather_device, shard_units
+    from opticommpy_b200.sharding import gather_device, run_concurrent, shard_units
     n_ch, sps, rs = 5, 8, 32e9
     fs = rs * sps
     sig, symb, grid, pulse, source = wdm_waveform(n_ch, 15, sps, seed=321)
@@ -263,18 +269,25 @@ def extra_cfg5_mc(torch, dist, world, rank, n_seeds=64, spans=3, hz=0.1):
     rec.symbRef = np.ascontiguousarray((txs / np.sqrt(np.mean(np.abs(txs) ** 2))).astype(np.complex64))
     rx_symbols_device(rows, float(grid[ch]), rec)  # warm-up
     mine = shard_units(n_seeds, rank, world)
+    nw = unit_workers()
+
+    def unit(i, spans_=None):
+        r = rows0.clone()
+        p = base.copy()
+        p.seed = 1000 + i
+        if spans_:
+            p.Ltotal = 80 * spans_
+        st = manakov_rows_device(r, p, +1)              # on-device Philox ASE noise, one Philox stream per seed and span
+        d_sym = rx_symbols_device(r, float(grid[ch]), rec)
+        return torch.tensor(ber_scalars_device(d_sym, rec), dtype=torch.float64, device="cuda"), st["steps"]
+
+    run_concurrent(lambda i: unit(i, 1), list(range(nw)), nw)  # warm-up of every worker stream (plans, tables, cuFFT handles)
     _sync(torch, dist, world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    local, steps = {}, 0
-    for i in mine:
-        rows.copy_(rows0)
-        p = base.copy()
-        p.seed = 1000 + i
-        st = manakov_rows_device(rows, p, +1)           # on-device Philox ASE noise, one stream per seed and span
-        steps += st["steps"]
-        d_sym = rx_symbols_device(rows, float(grid[ch]), rec)
-        local[i] = torch.tensor(ber_scalars_device(d_sym, rec), dtype=torch.float64, device="cuda")
+    done = run_concurrent(unit, mine, nw)  # up to nw seeds in flight on this GPU, one stream + plan each
+    local = {i: v[0] for i, v in done.items()}
+    steps = sum(v[1] for v in done.values())
     full = gather_device(local, n_seeds)  # 3 scalars per seed
     e1.record()
     _sync(torch, dist, world)
@@ -286,7 +299,7 @@ def extra_cfg5_mc(torch, dist, world, rank, n_seeds=64, spans=3, hz=0.1):
     return {"workload": f"cfg5: {n_seeds} ASE-noise seeds x 5-ch WDM DP-16QAM (N = 2^18, {spans} x 80 km, hz = {hz} km) manakovSSF + centre-channel "
                         "receiver (front end, matched filter, decimate, edc, nlms->dd-lms equalizer, bps) + on-device BER/SER/SNR",
             "input": source, "value": n * float(tot_steps.item()) / (ms * 1e-3) / 1e6, "unit": "Msamples/s (SSFM sample-steps, receiver time included)",
-            "seconds": ms * 1e-3, "seeds": n_seeds, "seeds_per_s": n_seeds / (ms * 1e-3),
+            "seconds": ms * 1e-3, "seeds": n_seeds, "seeds_per_s": n_seeds / (ms * 1e-3), "units_in_flight_per_gpu": nw,
             "shard_sizes": [len(shard_units(n_seeds, r, world)) for r in range(world)],
             "gathered": [int(v) for v in res.shape], "gather": "one all_gather of 3 float64 per seed",
             "ber_mean": float(res[:, 0].mean()), "ser_mean": float(res[:, 1].mean()),

@@ -1,20 +1,25 @@
 """Plan/workspace cache shared by the host-side mirrors.
 
-A plan (cuFFT handles + workspace partition) is created once per (device, N, rows) and kept in a
-small LRU; its device memory is a torch uint8 tensor so that all HBM use goes through one
-allocator.  Nothing here computes: every numeric operation is a C-ABI call.
+A plan (cuFFT handles + workspace partition + convergence mailbox) is created once per
+(device, stream, N, rows) and kept in a small LRU; its device memory is a torch uint8 tensor so that
+all HBM use goes through one allocator.  The stream is part of the key because a plan owns ONE
+workspace: host threads that propagate independent waveforms concurrently, each on its own CUDA
+stream (``sharding.run_concurrent``), get one plan each.  Nothing here computes: every numeric
+operation is a C-ABI call.
 """
 from __future__ import annotations
 
 import collections
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
 from . import _cabi
 
-_MAX_PLANS = 4
+_MAX_PLANS = 24  # far above the number of plans in use at once (<= 8 worker streams x a few geometries): only idle plans reach the LRU tail
+_lock = threading.Lock()
 ENGINES = {"auto": 0, "cufft": 1, "fused": 2}
 _default_engine = os.environ.get("OCB_ENGINE", "auto")
 
@@ -65,25 +70,33 @@ _plans: "collections.OrderedDict[tuple, SsfmPlan]" = collections.OrderedDict()
 
 
 def get_plan(N: int, rows: int, device: int | None = None) -> SsfmPlan:
+    """The plan of (device, current stream of that device, N, rows); created on first use."""
     torch = _cabi.require_cuda()
     if device is None:
         device = torch.cuda.current_device()
-    key = (int(device), int(N), int(rows))
-    plan = _plans.get(key)
-    if plan is None:
+    stream = int(torch.cuda.current_stream(device).cuda_stream)
+    key = (int(device), stream, int(N), int(rows))
+    with _lock:
+        plan = _plans.get(key)
+        if plan is not None:
+            _plans.move_to_end(key)
+            return plan
+        evicted = []
         while len(_plans) >= _MAX_PLANS:
-            _, old = _plans.popitem(last=False)
-            old.close()
-        plan = SsfmPlan(N, rows, device)
+            evicted.append(_plans.popitem(last=False)[1])
+    for old in evicted:  # an evicted plan is idle: its stream's owner is the thread asking for a new one, or it is stale
+        old.close()
+    plan = SsfmPlan(N, rows, device)
+    with _lock:
         _plans[key] = plan
-    else:
-        _plans.move_to_end(key)
     return plan
 
 
 def clear_plans() -> None:
-    while _plans:
-        _, p = _plans.popitem()
+    with _lock:
+        old = list(_plans.values())
+        _plans.clear()
+    for p in old:
         p.close()
 
 

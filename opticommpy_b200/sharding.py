@@ -88,6 +88,90 @@ def gather_results(local: dict, n_units: int, device=None):
     return out
 
 
+_worker_streams: dict = {}
+
+
+def run_concurrent(fn, units, workers: int = 4, cuda: bool = True):
+    """Run ``fn(unit)`` for every unit of this rank with up to ``workers`` units in flight on ONE GPU: one host thread
+    and one CUDA stream per worker, so that the kernels of independent small waveforms (N <= 2^18: a step-loop launch
+    fills a fraction of the 148 SMs and is a dependent chain through a few warps per SM) overlap on the device.
+
+    Every worker makes the caller's device current, runs its units inside ``torch.cuda.stream(own_stream)`` — this
+    package's entry points launch on the current stream and keep one plan / workspace per stream — and the streams are
+    ordered against the caller's stream by events on both sides (no host synchronisation): work enqueued by the caller
+    before the call is visible to the workers, and the caller's stream waits for all of them before it continues.
+    Returns ``{unit: result}``.  The first exception of a worker is re-raised after all workers have stopped.
+    ``cuda=False`` runs the same scheduler on plain host threads (tests of the host logic)."""
+    import queue
+    import threading
+
+    units = list(units)
+    out, errors = {}, []
+    if not units:
+        return out
+    workers = max(1, min(int(workers), len(units)))
+    if cuda:
+        import torch
+
+        dev = torch.cuda.current_device()
+        caller = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(caller)
+        # the same worker streams on every call: plans and cuFFT handles are cached per stream
+        pool = _worker_streams.setdefault(dev, [])
+        while len(pool) < workers:
+            pool.append(torch.cuda.Stream(device=dev))
+        streams = pool[:workers]
+    q = queue.SimpleQueue()
+    for u in units:
+        q.put(u)
+
+    def mark(x, stream):  # results allocated on a worker stream are handed to the caller's stream
+        import torch
+
+        if isinstance(x, torch.Tensor):
+            if x.is_cuda:
+                x.record_stream(stream)
+        elif isinstance(x, (tuple, list)):
+            for y in x:
+                mark(y, stream)
+        elif isinstance(x, dict):
+            for y in x.values():
+                mark(y, stream)
+
+    def work(w):
+        try:
+            if cuda:
+                torch.cuda.set_device(dev)  # a new thread starts on device 0
+                streams[w].wait_event(ready)
+            while not errors:
+                try:
+                    u = q.get_nowait()
+                except queue.Empty:
+                    return
+                if cuda:
+                    with torch.cuda.stream(streams[w]):
+                        r = fn(u)
+                    mark(r, caller)
+                else:
+                    r = fn(u)
+                out[u] = r
+        except BaseException as e:  # noqa: BLE001 - re-raised in the caller
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(w,), name=f"ocb-unit-worker-{w}") for w in range(workers)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if cuda:
+        for s in streams:
+            caller.wait_stream(s)
+    if errors:
+        raise errors[0]
+    return out
+
+
 def run_sharded(fn, units, *args, **kwargs):
     """Apply ``fn(unit, *args, **kwargs) -> ndarray`` to this rank's shard and gather everything."""
     mine = shard_units(len(units))

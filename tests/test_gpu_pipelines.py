@@ -104,3 +104,49 @@ def test_cfg5_receiver_and_error_counting_vs_oracle():
     ber, ser, snr = ber_scalars_device(d_sym, rec)
     assert abs(snr - float(np.mean(snr_o))) < 0.1
     assert abs(ber - float(np.mean(ber_o))) <= 2e-4 and ber < 1e-2
+
+
+def test_run_concurrent_units_equal_sequential_units():
+    """sharding.run_concurrent: independent seeded propagations + front end + EDC with several units in flight on one GPU
+    (one host thread, stream and plan per worker) give bit-identical results to the same units run one after the other."""
+    import torch
+    from opticommpy_b200.channels import manakov_rows_device
+    from opticommpy_b200.equalization import _edc_taps, edc_rows_device
+    from opticommpy_b200.pipelines import channel_frontend_device, upload_field
+    from opticommpy_b200.sharding import run_concurrent
+    n_ch, sps, rs = 3, 8, 32e9
+    fs = rs * sps
+    sig, symb, grid, pulse, _ = _wdm(n_ch, 13, sps, 5)           # N = 2^16
+    rows0 = upload_field(sig)
+    base = Bag(Fs=fs, Ltotal=160, Lspan=80, hz=1.0, alpha=0.2, D=16, gamma=1.3, Fc=193.1e12, amp="edfa", NF=4.5, maxIter=10,
+               tol=1e-5, nlprMethod=False, maxNlinPhaseRot=2e-2, seed=None)
+    h_edc, _, _ = _edc_taps(Bag(L=160, D=16, Fc=193.1e12, Rs=rs, Fs=2 * rs), 2 * rs)
+
+    def unit(i):
+        r = rows0.clone()
+        p = Bag(**base.__dict__)
+        p.seed = 77 + i                                           # on-device Philox noise keyed by the seed
+        st = manakov_rows_device(r, p, +1)
+        ch = channel_frontend_device(r, float(grid[1]), fs, pulse, sps, 2)
+        d_in = torch.view_as_real(ch).contiguous()
+        d_out = torch.empty_like(d_in)
+        keep = edc_rows_device(d_in, d_out, h_edc)
+        return d_out, st
+
+    units = list(range(6))
+    seq = {i: unit(i) for i in units}
+    torch.cuda.synchronize()
+    con = run_concurrent(unit, units, workers=3)
+    torch.cuda.synchronize()
+    assert sorted(con) == units
+    for i in units:
+        assert con[i][1] == seq[i][1]
+        assert torch.equal(con[i][0], seq[i][0]), f"unit {i} differs between concurrent and sequential execution"
+    assert not torch.equal(con[0][0], con[1][0])                  # different seeds, different noise
+    # a failing unit surfaces in the caller
+    def bad(i):
+        if i == 2:
+            raise ValueError("unit 2 failed")
+        return unit(i)
+    with pytest.raises(ValueError):
+        run_concurrent(bad, units, workers=3)

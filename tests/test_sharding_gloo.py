@@ -129,3 +129,38 @@ def test_ragged_dbp_pipeline_end_to_end():
         assert p.exitcode == 0
     assert sorted(len(m) for _, m, _ in res) == [1, 2]      # 3 channels over 2 ranks
     assert all(ok for _, _, ok in res)
+
+
+def test_run_concurrent_scheduler_on_host_threads():
+    """Host logic of sharding.run_concurrent (cuda=False): every unit runs exactly once, results are keyed by unit, at most
+    `workers` units are in flight, and the first exception of a worker reaches the caller."""
+    import threading
+    import time
+
+    from opticommpy_b200.sharding import run_concurrent
+    lock, state = threading.Lock(), {"now": 0, "peak": 0, "calls": 0}
+
+    def fn(u):
+        with lock:
+            state["now"] += 1
+            state["calls"] += 1
+            state["peak"] = max(state["peak"], state["now"])
+        time.sleep(0.01)
+        with lock:
+            state["now"] -= 1
+        return u * u
+
+    out = run_concurrent(fn, range(13), workers=3, cuda=False)
+    assert out == {u: u * u for u in range(13)}
+    assert state["calls"] == 13 and 1 <= state["peak"] <= 3
+    assert run_concurrent(fn, [], workers=3, cuda=False) == {}
+    assert run_concurrent(fn, [5], workers=8, cuda=False) == {5: 25}
+
+    def bad(u):
+        if u == 4:
+            raise KeyError("unit 4")
+        return u
+
+    import pytest
+    with pytest.raises(KeyError):
+        run_concurrent(bad, range(8), workers=2, cuda=False)
