@@ -113,6 +113,37 @@ def extra_cfg1(torch):
             "iterations": st["iterations"], "us_per_ssfm_step": 1e3 * ms / reps / st["steps"]}
 
 
+# ---- cfg2 waveforms in flight ---------------------------------------------------------------------------------------------
+def extra_cfg2_concurrent(torch, rows0, in_flight=(2, 3), spans=1):
+    """Several independent realisations of the cfg2 waveform (N = 2^20, one span = 1001 steps each) propagated at the same
+    time on ONE GPU through sharding.run_concurrent: one launch of the step loop is a single wave over the SMs whose
+    load / transform / store phases do not overlap, so independent waveforms on separate streams fill each other's gaps.
+    This is the Monte-Carlo / parameter-sweep regime, not the headline (which is one waveform per GPU)."""
+    import bench
+    from opticommpy_b200.channels import manakov_rows_device
+    from opticommpy_b200.sharding import run_concurrent
+    n = int(rows0.shape[1])
+    prm = bench.channel_param(spans)
+
+    def unit(i):
+        r = rows0.clone()
+        p = prm.copy() if hasattr(prm, "copy") else prm
+        return manakov_rows_device(r, p, +1)["steps"]
+
+    out = {"workload": f"cfg2 waveform, {spans} span(s) per realisation, R independent realisations in flight on one GPU "
+                       "(one host thread, stream and plan each)", "unit": "Msamples/s (aggregate)"}
+    for R in (1,) + tuple(in_flight):
+        run_concurrent(unit, list(range(R)), R)  # warm-up: plans and tables of the worker streams
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        done = run_concurrent(unit, list(range(2 * R)), R)
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"in_flight_{R}"] = n * sum(done.values()) / (e0.elapsed_time(e1) * 1e-3) / 1e6
+    return out
+
+
 # ---- cfg3: receiver chain --------------------------------------------------------------------------------------------------
 def extra_rx_chain(torch, peak_gbs, nsym_log2=21, cpu_nsym_log2=15):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
@@ -194,9 +225,12 @@ def extra_rx_chain(torch, peak_gbs, nsym_log2=21, cpu_nsym_log2=15):
 
 
 # ---- cfg4: per-channel DBP, channels sharded --------------------------------------------------------------------------------
-def unit_workers():
-    """Units (channels, seeds) kept in flight per GPU by sharding.run_concurrent in the sharded extras (OCB_UNIT_WORKERS)."""
-    return max(1, int(os.environ.get("OCB_UNIT_WORKERS", "4")))
+def unit_workers(n_units):
+    """Units (channels, seeds) kept in flight per GPU by sharding.run_concurrent in the sharded extras: the balanced
+    default (at most 8), or OCB_UNIT_WORKERS."""
+    from opticommpy_b200.sharding import balanced_workers
+    v = os.environ.get("OCB_UNIT_WORKERS")
+    return max(1, int(v)) if v else balanced_workers(max(1, n_units))
 
 
 def extra_cfg4_dbp(torch, dist, world, rank, spans=10, hz_dbp=0.8):
@@ -213,7 +247,7 @@ def extra_cfg4_dbp(torch, dist, world, rank, spans=10, hz_dbp=0.8):
     prm = Bag(Fs=2 * rs, Ltotal=80 * spans, Lspan=80, hz=hz_dbp, alpha=0.2, D=16, gamma=1.3, Fc=193.1e12, amp="edfa", NF=4.5,
               maxIter=10, tol=1e-5, nlprMethod=False, maxNlinPhaseRot=2e-2, seed=None)
     mine = shard_units(n_ch, rank, world)
-    nw = unit_workers()
+    nw = unit_workers(len(mine))
     unit = lambda k: dbp_channel_device(rows, float(grid[k]), fs, pulse, sps, prm)
     run_concurrent(unit, [n_ch // 2] * nw, nw)  # warm-up (plans and tables of every worker stream)
     _sync(torch, dist, world)
@@ -269,7 +303,7 @@ def extra_cfg5_mc(torch, dist, world, rank, n_seeds=64, spans=3, hz=0.1):
     rec.symbRef = np.ascontiguousarray((txs / np.sqrt(np.mean(np.abs(txs) ** 2))).astype(np.complex64))
     rx_symbols_device(rows, float(grid[ch]), rec)  # warm-up
     mine = shard_units(n_seeds, rank, world)
-    nw = unit_workers()
+    nw = unit_workers(len(mine))
 
     def unit(i, spans_=None):
         r = rows0.clone()
