@@ -236,8 +236,8 @@ def unit_workers(n_units):
 def extra_cfg4_dbp(torch, dist, world, rank, spans=10, hz_dbp=0.8):
     import bench
     from opticommpy_b200.channels import manakov_rows_device
-    from opticommpy_b200.pipelines import dbp_channel_device, upload_field
-    from opticommpy_b200.sharding import gather_device, run_concurrent, shard_units
+    from opticommpy_b200.pipelines import dbp_channel_device, dbp_channels_device, upload_field
+    from opticommpy_b200.sharding import gather_device, shard_units
     n_ch, sps, rs = 11, 16, 32e9
     fs = rs * sps
     sig, symb, grid, pulse, source = wdm_waveform(n_ch, 16, sps, seed=123)
@@ -248,12 +248,12 @@ def extra_cfg4_dbp(torch, dist, world, rank, spans=10, hz_dbp=0.8):
               maxIter=10, tol=1e-5, nlprMethod=False, maxNlinPhaseRot=2e-2, seed=None)
     mine = shard_units(n_ch, rank, world)
     nw = unit_workers(len(mine))
-    unit = lambda k: dbp_channel_device(rows, float(grid[k]), fs, pulse, sps, prm)
-    run_concurrent(unit, [n_ch // 2] * nw, nw)  # warm-up (plans and tables of every worker stream)
+    run = lambda units: dbp_channels_device(rows, grid, fs, pulse, sps, prm, units=units, workers=nw)
+    run([n_ch // 2] * nw)  # warm-up (plans and tables of every worker stream)
     _sync(torch, dist, world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    done = run_concurrent(unit, mine, nw)  # up to nw channels in flight on this GPU, one stream + plan each
+    done = run(mine)  # up to nw channels in flight on this GPU, one stream + plan each
     local = {k: v[0] for k, v in done.items()}
     steps = sum(v[1]["steps"] for v in done.values())
     full = gather_device(local, n_ch)  # the path's only collective: 11 x (2, 2^17) complex64 fields over NVLink
@@ -279,9 +279,9 @@ def extra_cfg5_mc(torch, dist, world, rank, n_seeds=64, spans=3, hz=0.1):
     import bench
     from opticommpy_b200.channels import manakov_rows_device
     from opticommpy_b200.core import symbolSync
-    from opticommpy_b200.pipelines import RxRecipe, ber_scalars_device, channel_frontend_device, rx_symbols_device, upload_field
+    from opticommpy_b200.pipelines import RxRecipe, channel_frontend_device, monte_carlo_ber_device, rx_symbols_device, upload_field
     from opticommpy_b200.equalization import edc_rows_device
-    from opticommpy_b200.sharding import gather_device, run_concurrent, shard_units
+    from opticommpy_b200.sharding import gather_device, shard_units
     n_ch, sps, rs = 5, 8, 32e9
     fs = rs * sps
     sig, symb, grid, pulse, source = wdm_waveform(n_ch, 15, sps, seed=321)
@@ -304,23 +304,14 @@ def extra_cfg5_mc(torch, dist, world, rank, n_seeds=64, spans=3, hz=0.1):
     rx_symbols_device(rows, float(grid[ch]), rec)  # warm-up
     mine = shard_units(n_seeds, rank, world)
     nw = unit_workers(len(mine))
-
-    def unit(i, spans_=None):
-        r = rows0.clone()
-        p = base.copy()
-        p.seed = 1000 + i
-        if spans_:
-            p.Ltotal = 80 * spans_
-        st = manakov_rows_device(r, p, +1)              # on-device Philox ASE noise, one Philox stream per seed and span
-        d_sym = rx_symbols_device(r, float(grid[ch]), rec)
-        return torch.tensor(ber_scalars_device(d_sym, rec), dtype=torch.float64, device="cuda"), st["steps"]
-
-    run_concurrent(lambda i: unit(i, 1), list(range(nw)), nw)  # warm-up of every worker stream (plans, tables, cuFFT handles)
+    warm = base.copy()
+    warm.Ltotal = 80
+    monte_carlo_ber_device(rows0, [1000 + i for i in range(nw)], warm, float(grid[ch]), rec, workers=nw)  # warm-up of every worker stream
     _sync(torch, dist, world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    done = run_concurrent(unit, mine, nw)  # up to nw seeds in flight on this GPU, one stream + plan each
-    local = {i: v[0] for i, v in done.items()}
+    done = monte_carlo_ber_device(rows0, [1000 + i for i in mine], base, float(grid[ch]), rec, workers=nw)  # up to nw seeds in flight
+    local = {i: done[1000 + i][0] for i in mine}
     steps = sum(v[1] for v in done.values())
     full = gather_device(local, n_seeds)  # 3 scalars per seed
     e1.record()

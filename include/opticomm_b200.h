@@ -17,6 +17,11 @@
  *     optic/models/channels.py:364-365).
  *   - "_host" variants take HOST pointers and perform H2D / D2H themselves (this is the
  *     call the end-to-end number in bench.py goes through).
+ *   - threads: the library keeps no global mutable state apart from a mutex-protected cache of
+ *     cuFFT handles keyed by (device, stream, geometry).  Calls from different host threads are
+ *     independent as long as every thread uses its own stream and its own ocb_ssfm_plan (a plan
+ *     owns one workspace and one convergence mailbox): this is how several independent waveforms
+ *     are kept in flight on one GPU (opticommpy_b200.sharding.run_concurrent).
  */
 #ifndef OPTICOMM_B200_H
 #define OPTICOMM_B200_H

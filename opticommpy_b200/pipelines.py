@@ -141,3 +141,34 @@ def ber_scalars_device(d_sym, recipe, discard=2000):
     a, b = discard, L - discard
     ber, ser, snr = fastBERcalc(d_sym[a:b].contiguous(), ref[a:b].contiguous(), recipe.M, "qam")
     return float(np.mean(ber)), float(np.mean(ser)), float(np.mean(snr))
+
+
+def dbp_channels_device(rows_wdm, ch_freqs, Fs, pulse, SpSin, paramDBP, units=None, workers=None, SpSout=2):
+    """cfg4 on one GPU: ``dbp_channel_device`` for the channels ``units`` (indices into ``ch_freqs``; default: all) with
+    several channels in flight (``sharding.run_concurrent``: one host thread, CUDA stream and plan per worker; at N = 2^17
+    one back-propagation alone uses a fraction of the SMs).  Returns ``{k: ((2, N') complex64 CUDA tensor, DBP stats)}``."""
+    from .sharding import run_concurrent
+    units = list(range(len(ch_freqs))) if units is None else list(units)
+    return run_concurrent(lambda k: dbp_channel_device(rows_wdm, float(ch_freqs[k]), Fs, pulse, SpSin, paramDBP, SpSout),
+                          units, workers)
+
+
+def monte_carlo_ber_device(rows0, seeds, param, ch_freq, recipe, workers=None, discard=2000):
+    """cfg5 on one GPU: for every ASE-noise seed in ``seeds`` propagate a private copy of the noiseless transmit field
+    ``rows0`` ((2, N) complex64 CUDA) with ``param`` (``param.seed`` replaced by the seed: on-device Philox streams), run the
+    receiver of ``recipe`` on channel ``ch_freq`` and count errors on the device; several seeds in flight
+    (``sharding.run_concurrent``).  Returns ``{seed: (float64 CUDA tensor [BER, SER, SNR dB], executed SSFM steps)}``."""
+    torch = _cabi.require_cuda()
+    from .sharding import run_concurrent
+    if recipe.d_ref is None:  # created once, before the workers start
+        recipe.d_ref = _to_device(torch, recipe.symbRef.view(np.float32)).reshape(1, recipe.symbRef.shape[0], 2, 2)
+
+    def unit(seed):
+        r = rows0.clone()
+        p = Bag(**param.__dict__)
+        p.seed = int(seed)
+        st = manakov_rows_device(r, p, +1)
+        d_sym = rx_symbols_device(r, float(ch_freq), recipe)
+        return torch.tensor(ber_scalars_device(d_sym, recipe, discard), dtype=torch.float64, device=r.device), st["steps"]
+
+    return run_concurrent(unit, list(seeds), workers)

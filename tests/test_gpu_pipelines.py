@@ -104,6 +104,17 @@ def test_cfg5_receiver_and_error_counting_vs_oracle():
     ber, ser, snr = ber_scalars_device(d_sym, rec)
     assert abs(snr - float(np.mean(snr_o))) < 0.1
     assert abs(ber - float(np.mean(ber_o))) <= 2e-4 and ber < 1e-2
+    # the sweep driver: several Philox-seeded units in flight == the same units one at a time (bit-identical scalars)
+    from opticommpy_b200.pipelines import monte_carlo_ber_device
+    rows0 = upload_field(sig)
+    seeds = [11, 12, 13]
+    con = monte_carlo_ber_device(rows0, seeds, prm, float(grid[ch]), rec, workers=3)
+    seq = monte_carlo_ber_device(rows0, seeds, prm, float(grid[ch]), rec, workers=1)
+    for sd in seeds:
+        assert con[sd][1] == seq[sd][1] == 80
+        assert torch.equal(con[sd][0], seq[sd][0])
+        assert abs(float(con[sd][0][2]) - snr) < 0.5                 # another noise realisation of the same link
+    assert not torch.equal(con[11][0], con[12][0])
 
 
 def test_run_concurrent_units_equal_sequential_units():
