@@ -108,9 +108,26 @@ def extra_cfg1(torch):
         e1.record()
         torch.cuda.synchronize()
         ms += e0.elapsed_time(e1)
-    return {"workload": "cfg1: single-channel 2-pol manakovSSF, 2^16 samples, 1 span of 80 km, hz = 0.8 km, fixed step",
-            "value": n * st["steps"] * reps / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "steps": st["steps"],
-            "iterations": st["iterations"], "us_per_ssfm_step": 1e3 * ms / reps / st["steps"]}
+    res = {"workload": "cfg1: single-channel 2-pol manakovSSF, 2^16 samples, 1 span of 80 km, hz = 0.8 km, fixed step",
+           "value": n * st["steps"] * reps / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "steps": st["steps"],
+           "iterations": st["iterations"], "us_per_ssfm_step": 1e3 * ms / reps / st["steps"]}
+    # the same propagation for 8 independent waveforms in flight on the GPU (sharding.run_concurrent): at this size one
+    # waveform is a latency chain through 64 small CTAs per launch, the chip's throughput shows with several at once
+    from opticommpy_b200.sharding import run_concurrent
+
+    def unit(i):
+        r = rows0.clone()
+        return manakov_rows_device(r, prm, +1)["steps"]
+
+    run_concurrent(unit, list(range(8)), 8)
+    torch.cuda.synchronize()
+    e0.record()
+    done = run_concurrent(unit, list(range(32)), 8)
+    e1.record()
+    torch.cuda.synchronize()
+    res["eight_in_flight"] = {"value": n * sum(done.values()) / (e0.elapsed_time(e1) * 1e-3) / 1e6, "unit": "Msamples/s (aggregate)",
+                              "waveforms": 32, "in_flight": 8}
+    return res
 
 
 # ---- cfg2 waveforms in flight ---------------------------------------------------------------------------------------------
