@@ -320,6 +320,29 @@ int ocb_xcorr_peak_run(const void* a_rows, int nA, int64_t La, const void* b_row
 int ocb_sync_apply_run(const void* tx_dev, void* out_dev, int64_t L, int nCols, const int32_t* swap_dev,
                        const void* rot_dev, const int32_t* conj_dev, const int64_t* delay_dev, void* stream);
 
+/* ---- WDM transmitter (input generation at scale) -------------------------------
+ * Replaces the per-sample work of optic.models.tx.simpleWDMTx (optic/models/tx.py:42-228); the symbol draw (numpy's
+ * legacy generator, optic/comm/sources.py:167-211) and the laser phase-noise walk stay on the host.
+ *   ocb_upsample_run       : rows_out[r][SpS*k] = sym_rows[r][k], zeros in between (optic/dsp/core.py:395-432);
+ *                            sym_rows planar [nRows][nSym] complex64, rows_out [nRows][nSym*SpS].  The pulse-shaping
+ *                            filter is then ocb_edc_run with the pulse taps (firFilter, core.py:87-125).
+ *   ocb_wdm_tx_combine_run : shaped_rows planar [nCh*nPol][N] complex64 (row = ch*nPol + mode), per row
+ *                            s / max|s| (tx.py:196) -> iqm(LO, mzmScale * s) (optic/models/devices.py:147-216, calcMZM /
+ *                            calcPM optic/dsp/core.py:1075-1130) -> sqrt(P_ch / nPol) * pnorm (tx.py:206, core.py:702-717)
+ *                            -> freqShift by ch_freq_hz[ch] (core.py:1050-1072) -> summed over the channels in ascending
+ *                            order into out_rows planar [nPol][N] complex64 (tx.py:208).
+ *                            lo_rows: [nCh][N] complex64 LO fields exp(j phi_pn) or NULL for an ideal laser (linewidth 0);
+ *                            ch_power_w / ch_freq_hz: HOST arrays of nCh doubles.                                     */
+typedef struct {
+    double mzmScale; /* Vrf / Vpi scale of the driving signal (tx.py:64) */
+    double Vpi, VbI, VbQ, Vphi, ERI, ERQ; /* iqm parameters, defaults 2, -2, -2, 1, 60, 60 (devices.py:181-186) */
+} ocb_wdm_tx_params;
+int ocb_upsample_run(const void* sym_rows, int nRows, int64_t nSym, int SpS, void* rows_out, void* stream);
+int64_t ocb_wdm_tx_workspace_bytes(int nCh, int nPol);
+int ocb_wdm_tx_combine_run(const void* shaped_rows, const void* lo_rows, int nCh, int nPol, int64_t N,
+                           const ocb_wdm_tx_params* q, const double* ch_power_w, const double* ch_freq_hz, double Fs,
+                           void* out_rows, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,10 @@ class NlseParams(C.Structure):
     ]
 
 
+class WdmTxParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("mzmScale", "Vpi", "VbI", "VbQ", "Vphi", "ERI", "ERQ")]
+
+
 _vp, _i, _i64, _d, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_uint64
 
 # name -> (restype, argtypes); must list every symbol declared in include/opticomm_b200.h
@@ -99,6 +103,10 @@ SIGNATURES = {
     "ocb_xcorr_workspace_bytes": (_i64, [_i, _i64, _i, _i64]),
     "ocb_xcorr_peak_run": (_i, [_vp, _i, _i64, _vp, _i, _i64, C.POINTER(C.c_int64), C.POINTER(C.c_double), _vp, _i64, _vp]),
     "ocb_sync_apply_run": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ocb_upsample_run": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "ocb_wdm_tx_workspace_bytes": (_i64, [_i, _i]),
+    "ocb_wdm_tx_combine_run": (_i, [_vp, _vp, _i, _i, _i64, C.POINTER(WdmTxParams), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   _d, _vp, _vp, _i64, _vp]),
     "ocb_min_euclid": (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp, _vp]),
     "ocb_ber_workspace_bytes": (_i64, [_i]),
     "ocb_ber_count": (_i, [_vp, _vp, _i, _i64, _i, _vp, _i, _i, _d, C.POINTER(C.c_double), C.POINTER(C.c_double),
