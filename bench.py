@@ -510,7 +510,8 @@ def main():
         if not args.no_extras and world == 1:
             import bench_extras as bx
             for name, fn in (("cfg1", lambda: bx.extra_cfg1(torch)), ("rx_chain", lambda: bx.extra_rx_chain(torch, peak)),
-                             ("cfg2_concurrent", lambda: bx.extra_cfg2_concurrent(torch, rows0))):
+                             ("cfg2_concurrent", lambda: bx.extra_cfg2_concurrent(torch, rows0)),
+                             ("wdm_tx", lambda: bx.extra_wdm_tx(torch))):
                 try:
                     line[name] = fn()
                 except Exception as e:  # an extra must never take the headline down

@@ -7,6 +7,7 @@ None of them changes the headline numbers; each is bounded to a few seconds of G
   cfg4_dbp : 11-channel WDM field after the cfg2 link, per-channel front end + manakovDBP, channels sharded over the ranks
   cfg5_mc  : 64 ASE-noise seeds x 5-channel WDM SSFM + receiver + on-device error counting, seeds sharded over the ranks,
              three scalars per seed gathered with one all_gather
+  cfg2_concurrent : independent cfg2 realisations in flight on one GPU ; wdm_tx : the device-side transmitter (simpleWDMTx)
 """
 import os
 import sys
@@ -28,8 +29,8 @@ class Bag:
 # ---- WDM transmitter input (host side, outside every timed region) -----------------------------------------------------
 def wdm_waveform(n_ch, nsym_log2, sps, seed=123, power_dbm=-2.0, spacing=37.5e9, rs=32e9):
     """(sig (N, 2) complex128, symb (nSym, 2, nCh), freqGrid, pulse, source): the reference's own simpleWDMTx
-    (optic/models/tx.py:42-228, imported from baseline/_ref or /root/reference) when it can be imported, else a synthetic
-    stand-in of the same shape (Nyquist-shaped DP-16QAM channels on the same grid)."""
+    (optic/models/tx.py:42-228, imported from baseline/_ref or /root/reference) when it can be imported, else the product's
+    device transmitter opticommpy_b200.tx.simpleWDMTx (the same symbols for the same seed, the field within 2e-6)."""
     import bench
     ref = bench.import_reference()
     nsym = 1 << nsym_log2
@@ -50,26 +51,56 @@ def wdm_waveform(n_ch, nsym_log2, sps, seed=123, power_dbm=-2.0, spacing=37.5e9,
             src_err = f" (simpleWDMTx failed: {e})"
     else:
         src_err = ""
-    rng = np.random.default_rng(seed)
-    c = np.array([a + 1j * b for a in (-3, -1, 1, 3) for b in (-3, -1, 1, 3)]) / np.sqrt(10)
-    n = nsym * sps
-    f = np.fft.fftfreq(n)
-    shape = (np.abs(f) < 0.5 / sps).astype(float)           # brick-wall Nyquist pulse at the symbol rate
-    grid = (np.arange(n_ch) - (n_ch - 1) / 2) * spacing
-    fs = rs * sps
-    sig = np.zeros((n, 2), dtype=complex)
-    symb = np.zeros((nsym, 2, n_ch), dtype=complex)
-    t = np.arange(n) / fs
-    for k in range(n_ch):
-        s = c[rng.integers(0, 16, size=(nsym, 2))]
-        symb[:, :, k] = s
-        up = np.zeros((n, 2), dtype=complex)
-        up[::sps] = s
-        x = np.fft.ifft(np.fft.fft(up, axis=0) * shape[:, None], axis=0)
-        x *= np.sqrt(10 ** (power_dbm / 10) * 1e-3 / np.mean(np.sum(np.abs(x) ** 2, axis=1)))
-        sig += x * np.exp(2j * np.pi * grid[k] * t)[:, None]
-    taps = np.real(np.fft.fftshift(np.fft.ifft(shape)))[n // 2 - 512:n // 2 + 512]
-    return sig, symb, grid, taps / np.max(np.abs(taps)), "synthetic Nyquist-shaped DP-16QAM stand-in" + src_err
+    # no reference on this box: the product's own transmitter (same symbols for the same seed, field within 2e-6)
+    from opticommpy_b200.tx import pulseShape as pulse_b200, simpleWDMTx as tx_b200
+    p = Bag(M=16, Rs=rs, SpS=sps, nBits=4 * nsym, pulseType="rrc", nFilterTaps=1024, pulseRollOff=0.01, powerPerChannel=power_dbm,
+            nChannels=n_ch, Fc=193.1e12, wdmGridSpacing=spacing, nPolModes=2, seed=seed, prgsBar=False)
+    sig, symb, p = tx_b200(p)
+    pulse = pulse_b200(Bag(pulseType="rrc", nFilterTaps=1024, rollOff=0.01, SpS=sps))
+    return sig, symb, np.asarray(p.wdmFreqGrid), pulse / np.max(np.abs(pulse)), "opticommpy_b200.tx.simpleWDMTx (device)" + src_err
+
+
+# ---- transmitter -------------------------------------------------------------------------------------------------------------
+def extra_wdm_tx(torch, n_ch=11, nsym_log2=16, sps=16, cpu_nsym_log2=12):
+    """The cfg2 / cfg4 input generator: 11-channel DP-16QAM, 2^16 symbols x 16 SpS = 2^20 samples per polarisation, through
+    opticommpy_b200.tx.wdm_tx_rows_device (output stays on the GPU), next to the unmodified reference's simpleWDMTx on a
+    bounded sample (one core) with the agreement of the two fields on that sample."""
+    import bench
+    from opticommpy_b200.tx import simpleWDMTx, wdm_tx_rows_device
+    kw = dict(M=16, Rs=32e9, SpS=sps, pulseType="rrc", nFilterTaps=1024, pulseRollOff=0.01, powerPerChannel=-2.0, nChannels=n_ch,
+              Fc=193.1e12, wdmGridSpacing=37.5e9, nPolModes=2, seed=123, prgsBar=False)
+    nsym = 1 << nsym_log2
+    wdm_tx_rows_device(Bag(nBits=4 * nsym, **kw))  # warm-up (cuFFT plans, allocator)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rows, symb, _ = wdm_tx_rows_device(Bag(nBits=4 * nsym, **kw))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    units = n_ch * 2 * nsym * sps  # (channel, mode) samples shaped and modulated
+    res = {"workload": f"simpleWDMTx: {n_ch}-ch DP-16QAM, 2^{nsym_log2} symbols x {sps} SpS per (channel, mode), rrc 1024 taps",
+           "seconds": dt, "value": units / dt / 1e6, "unit": "M (channel, mode) samples/s, host symbol draw + upload included",
+           "output": [int(v) for v in rows.shape]}
+    ref = bench.import_reference()
+    if ref is not None:
+        try:
+            from optic.models.tx import simpleWDMTx as tx_ref
+            _, parameters, where = ref
+            n_cpu = 1 << cpu_nsym_log2
+            p = parameters()
+            for k, v in kw.items():
+                setattr(p, k, v)
+            p.nBits = 4 * n_cpu
+            t0 = time.perf_counter()
+            sig_ref, symb_ref, _ = tx_ref(p)
+            t_ref = time.perf_counter() - t0
+            sig_dev, symb_dev, _ = simpleWDMTx(Bag(nBits=4 * n_cpu, **kw))
+            res["cpu_baseline"] = {"kind": "reference", "cores": 1, "sample": f"2^{cpu_nsym_log2} symbols per (channel, mode), {where}",
+                                   "value": n_ch * 2 * n_cpu * sps / t_ref / 1e6, "seconds": t_ref,
+                                   "rel_l2_device_vs_reference": float(np.linalg.norm(sig_dev - sig_ref) / np.linalg.norm(sig_ref)),
+                                   "symbols_identical": bool(np.array_equal(symb_dev, symb_ref))}
+        except Exception as e:
+            res["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    return res
 
 
 def _sync(torch, dist, world):
