@@ -186,10 +186,14 @@ def run_concurrent(fn, units, workers: int | None = None, cuda: bool = True):
     return out
 
 
-def run_sharded(fn, units, *args, **kwargs):
-    """Apply ``fn(unit, *args, **kwargs) -> ndarray`` to this rank's shard and gather everything."""
+def run_sharded(fn, units, *args, in_flight: int = 1, **kwargs):
+    """Apply ``fn(unit, *args, **kwargs) -> ndarray`` to this rank's shard and gather everything.  ``in_flight`` > 1 keeps
+    that many of the rank's units in flight on its GPU (``run_concurrent``); 1 runs them one after the other."""
     mine = shard_units(len(units))
-    local = {i: fn(units[i], *args, **kwargs) for i in mine}
+    if in_flight > 1 and len(mine) > 1:
+        local = run_concurrent(lambda i: fn(units[i], *args, **kwargs), mine, in_flight)
+    else:
+        local = {i: fn(units[i], *args, **kwargs) for i in mine}
     return gather_results(local, len(units))
 
 
