@@ -115,3 +115,36 @@ def pdmCoherentReceiver(Es, Elo, paramFE, paramPD=None):
     d_out = torch.empty((N, 2, 2), dtype=torch.float64, device="cuda")
     _cabi.check(lib.ocb_unpack_fields(_ptr(d_S), N, 2, 0, _ptr(d_out), _cabi.OCB_C128, st), "ocb_unpack_fields")
     return d_out.cpu().numpy().view(np.complex128).reshape(N, 2)  # complex128 like the reference's sI + 1j*sQ
+
+
+def basicLaserModel(param=None):
+    """
+    Laser field with random-walk phase noise and RIN (optic/models/devices.py:729-791): P [10 dBm], lw [1 kHz],
+    RIN_var [1e-20], Fs, Ns [1000], seed [None], freqShift [0 Hz].  Returns the (Ns,) complex128 field
+    ``sqrt(P + dP) exp(j (2 pi freqShift t + phi_pn))``.
+
+    A host-side input generator, kept for drop-in completeness of the receiver notebooks: both noise processes come from
+    numpy's legacy generator (seed for the phase walk, seed + 73 for the RIN), so a seeded call returns the reference's
+    local-oscillator field.  A noiseless CW LO needs no array at all: ``pdm_frontend_rows_device(..., d_Elo=None)``
+    generates it inside the front-end kernel.
+    """
+    from .tx import phaseNoise
+    try:
+        Fs = param.Fs
+    except AttributeError:
+        logg.error("Simulation sampling frequency (Fs) not provided.")
+        raise NameError("name 'Fs' is not defined") from None  # the reference dies on the unbound name (devices.py:779)
+    P = getattr(param, "P", 10)
+    lw = getattr(param, "lw", 1e3)
+    RIN_var = getattr(param, "RIN_var", 1e-20)
+    Ns = int(getattr(param, "Ns", 1000))
+    seed = getattr(param, "seed", None)
+    freqShift = getattr(param, "freqShift", 0)
+    pn = phaseNoise(lw, Ns, 1 / Fs, seed)
+    if seed is None:
+        s = np.sqrt(RIN_var / 2)
+        deltaP = np.random.normal(0, s, pn.shape) + 1j * np.random.normal(0, s, pn.shape)  # core.py:758-763, global stream
+    else:
+        deltaP = _engine.legacy_complex_noise(pn.shape, RIN_var, seed + 73)
+    fo = 2 * np.pi * freqShift * np.arange(Ns) / Fs if freqShift != 0 else 0
+    return np.sqrt(10 ** (P / 10) * 1e-3 + deltaP) * np.exp(1j * (fo + pn))

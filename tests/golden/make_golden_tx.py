@@ -22,7 +22,7 @@ import numpy as np  # noqa: E402
 
 from optic.comm.sources import symbolSource  # noqa: E402
 from optic.dsp.core import phaseNoise, pulseShape  # noqa: E402
-from optic.models.devices import iqm  # noqa: E402
+from optic.models.devices import basicLaserModel, iqm  # noqa: E402
 from optic.models.tx import simpleWDMTx  # noqa: E402
 from optic.utils import parameters  # noqa: E402
 
@@ -48,6 +48,14 @@ rng = np.random.default_rng(3)
 u = 0.5 * (rng.uniform(-1, 1, 2000) + 1j * rng.uniform(-1, 1, 2000))
 G["iqm_u"] = u
 G["iqm_out"] = iqm(np.exp(1j * G["pn"][:2000]), u)
+
+# basicLaserModel: LO with linewidth, RIN and a frequency shift; and the ideal CW case
+pl = parameters()
+pl.P, pl.lw, pl.RIN_var, pl.Fs, pl.Ns, pl.seed, pl.freqShift = 10, 100e3, 1e-20, 512e9, 5000, 789, 37.5e9 - 128e6
+G["laser_pn"] = basicLaserModel(pl)
+pl2 = parameters()
+pl2.P, pl2.lw, pl2.RIN_var, pl2.Fs, pl2.Ns, pl2.seed = 7, 0.0, 0, 64e9, 1000, 1
+G["laser_cw"] = basicLaserModel(pl2)
 
 # simpleWDMTx: dual-pol 5-channel DP-16QAM (cfg5 shape, shorter), single-pol 3-channel QPSK with a laser linewidth and
 # per-channel powers, even channel count

@@ -36,3 +36,13 @@ def test_pulse_shape_and_phase_noise(gtx):
         pulseShape(Bag(pulseType="duobinary"))
     assert np.allclose(phaseNoise(100e3, 4096, 1 / 512e9, seed=5), gtx["pn"], rtol=1e-12, atol=1e-15)
     assert np.array_equal(phaseNoise(0.0, 7, 1e-12, seed=1), np.zeros(7))
+
+
+def test_basic_laser_model(gtx):
+    from opticommpy_b200.devices import basicLaserModel
+    got = basicLaserModel(Bag(P=10, lw=100e3, RIN_var=1e-20, Fs=512e9, Ns=5000, seed=789, freqShift=37.5e9 - 128e6))
+    assert got.dtype == np.complex128 and np.allclose(got, gtx["laser_pn"], rtol=1e-12, atol=1e-15)
+    cw = basicLaserModel(Bag(P=7, lw=0.0, RIN_var=0, Fs=64e9, Ns=1000, seed=1))
+    assert np.allclose(cw, gtx["laser_cw"], rtol=1e-14, atol=0)
+    with pytest.raises(NameError):
+        basicLaserModel(Bag(P=0))
