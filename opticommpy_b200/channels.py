@@ -124,7 +124,8 @@ def _manakov_engine(Ei, param, direction, *, alpha_lin, beta2, Fs, noise_var=0.0
             f"({stats.nonconverged} steps)"
         )
     param._b200_stats = {"steps": int(stats.steps), "iterations": int(stats.iterations),
-                         "nonconverged": int(stats.nonconverged), "last_lim": float(stats.last_lim)}
+                         "nonconverged": int(stats.nonconverged), "last_lim": float(stats.last_lim),
+                         "z_last_step": float(stats.z_last_step)}
     if saveSpanN:
         Ech = np.zeros((N, C2 * len(saveSpanN)), dtype=out_dtype)
         for i in range(len(hits)):
@@ -171,7 +172,7 @@ def manakov_rows_device(rows, param, direction=+1, noise_rows=None):
             "ocb_manakov_run",
         )
     return {"steps": int(stats.steps), "iterations": int(stats.iterations), "nonconverged": int(stats.nonconverged),
-            "last_lim": float(stats.last_lim)}
+            "last_lim": float(stats.last_lim), "z_last_step": float(stats.z_last_step)}
 
 
 def manakovSSF(Ei, param):

@@ -204,6 +204,7 @@ def manakov(Ei, cfg: FiberConfig, direction=+1, stats=None):
             rec += 1
     if stats is not None:
         stats["steps"], stats["iterations"] = n_steps, n_iters
+        stats["z_last_step"] = float(h)
     if save:
         return snaps
     out = np.empty(Ei.shape, dtype=np.complex128)

@@ -197,3 +197,26 @@ def test_missing_fs_and_bad_amp(api, golden):
         api.manakovSSF(golden["mk_in"], Bag(Ltotal=80))
     with pytest.raises(AssertionError):
         api.manakovSSF(golden["mk_in"], Bag(Fs=64e9, NF=2.0, Ltotal=80, prgsBar=False))
+
+
+def test_adaptive_step_wdm_field_vs_oracle_within_the_controller_sensitivity():
+    """nlprMethod=True on an 11-channel WDM field, one 50 km span (54 steps growing from 0.36 to 2.4 km): the step sizes agree
+    with the float64 oracle to 1e-5 over the first half of the span and drift apart by percent over the last steps (the
+    controller amplifies complex64 rounding, tests/test_oracle_golden.py::test_adaptive_step_controller_...), so the field
+    is compared at the stated 3e-3; the same field in fixed-step mode agrees to 1e-5.  Step and iteration counts are equal."""
+    from opticommpy_b200.channels import manakovSSF
+    from opticommpy_b200.tx import simpleWDMTx
+    from oracle import fiber_oracle as fo
+    sig, _, _ = simpleWDMTx(Bag(M=16, Rs=32e9, SpS=16, nBits=4 * 4096, pulseType="rrc", nFilterTaps=1024, pulseRollOff=0.01,
+                                powerPerChannel=-2, nChannels=11, wdmGridSpacing=37.5e9, nPolModes=2, seed=123, prgsBar=False))
+    for adaptive, tol_l2 in ((True, 3e-3), (False, 1e-5)):
+        p = Bag(Fs=512e9, Ltotal=50, Lspan=50, alpha=0.2, D=16, gamma=1.3, Fc=193.1e12, hz=0.5, maxIter=5, tol=1e-5,
+                nlprMethod=adaptive, maxNlinPhaseRot=2e-2, amp="ideal", NF=4.5, seed=None, prgsBar=False, saveSpanN=[],
+                returnParameters=False, prec=np.complex128)
+        y = manakovSSF(sig, p)
+        st = {}
+        yo = fo.manakov(sig, fo.FiberConfig(Fs=512e9, Ltotal=50, Lspan=50, hz=0.5, maxIter=5, tol=1e-5, maxNlinPhaseRot=2e-2,
+                                            amp="ideal", seed=None, nlprMethod=adaptive), stats=st)
+        assert p._b200_stats["steps"] == st["steps"] and p._b200_stats["iterations"] == st["iterations"]
+        assert rel_l2(y, yo) < tol_l2, (adaptive, rel_l2(y, yo))
+        assert abs(np.sum(np.abs(y) ** 2) / np.sum(np.abs(yo) ** 2) - 1) < 1e-5

@@ -180,3 +180,28 @@ def test_oracle_cfg3_chain_vs_reference():
     y3 = out[0] if isinstance(out, tuple) else out
     d = np.argmin(np.abs(y3[..., None] - c), axis=-1).astype(np.uint8)
     assert not (d != g["cpr_dec"]).any()
+
+
+def test_adaptive_step_controller_amplifies_rounding_level_perturbations():
+    """Why the stated tolerance of the adaptive-step mode (nlprMethod=True) is 3e-3 per span and not 1e-5: the step-size rule
+    hz = maxNlinPhaseRot / max(phi) (channels.py:392-397) feeds the PEAK power of a noise-like WDM field back into the step
+    grid.  In the float64 restatement of the reference itself, a 1e-7 relative perturbation of the input — the size of one
+    complex64 rounding — changes the last step sizes by percent and the output by several 1e-4, while the fixed-step mode
+    passes the same perturbation through unamplified.  Any complex64 implementation inherits this; both outputs are equally
+    accurate solutions of the same equation on slightly different grids."""
+    from oracle import fiber_oracle as fo
+    from oracle import tx_oracle as to
+    sig, _, _ = to.simple_wdm_tx(M=16, Rs=32e9, SpS=16, nBits=4 * 2048, nFilterTaps=1024, pulseRollOff=0.01, powerPerChannel=-2,
+                                 nChannels=11, wdmGridSpacing=37.5e9, nPolModes=2, seed=123)
+    rng = np.random.default_rng(0)
+    pert = sig * (1 + 1e-7 * (rng.normal(size=sig.shape) + 1j * rng.normal(size=sig.shape)))
+    kw = dict(Fs=512e9, Ltotal=50, Lspan=50, hz=0.5, maxIter=5, tol=1e-5, maxNlinPhaseRot=2e-2, amp="ideal", seed=None)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    s0, s1 = {}, {}
+    ya = fo.manakov(sig, fo.FiberConfig(nlprMethod=True, **kw), stats=s0)
+    yb = fo.manakov(pert, fo.FiberConfig(nlprMethod=True, **kw), stats=s1)
+    yc = fo.manakov(sig, fo.FiberConfig(nlprMethod=False, **kw))
+    yd = fo.manakov(pert, fo.FiberConfig(nlprMethod=False, **kw))
+    assert rel(yd, yc) < 1e-6                         # fixed step: the perturbation passes through
+    assert 3e-5 < rel(yb, ya) < 3e-3                  # adaptive step: amplified by three to four orders of magnitude
+    assert abs(s0["z_last_step"] - s1["z_last_step"]) > 1e-4   # the step grids have drifted apart [km]
