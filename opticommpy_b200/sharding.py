@@ -89,6 +89,7 @@ def gather_results(local: dict, n_units: int, device=None):
 
 
 _worker_streams: dict = {}
+_pool_lock = None  # created on first use: one run_concurrent at a time per process (the worker streams are shared)
 
 
 MAX_WORKERS = 8
@@ -115,6 +116,7 @@ def run_concurrent(fn, units, workers: int | None = None, cuda: bool = True):
     ordered against the caller's stream by events on both sides (no host synchronisation): work enqueued by the caller
     before the call is visible to the workers, and the caller's stream waits for all of them before it continues.
     Returns ``{unit: result}``.  The first exception of a worker is re-raised after all workers have stopped.
+    One call at a time per process (a second caller waits); ``fn`` must not call ``run_concurrent`` itself.
     ``cuda=False`` runs the same scheduler on plain host threads (tests of the host logic)."""
     import queue
     import threading
@@ -173,11 +175,15 @@ def run_concurrent(fn, units, workers: int | None = None, cuda: bool = True):
         except BaseException as e:  # noqa: BLE001 - re-raised in the caller
             errors.append(e)
 
+    global _pool_lock
+    if _pool_lock is None:
+        _pool_lock = threading.Lock()
     threads = [threading.Thread(target=work, args=(w,), name=f"ocb-unit-worker-{w}") for w in range(workers)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    with _pool_lock:  # a second caller (another host thread) waits: the cached worker streams and their plans are not shared
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
     if cuda:
         for s in streams:
             caller.wait_stream(s)
