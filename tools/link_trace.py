@@ -3,6 +3,8 @@ reference (--impl reference: CPU, build container) or this package (--impl b200:
 
     python tools/link_trace.py --impl reference --out scratch_ref.npz     # here (CPU)
     python tools/link_trace.py --impl b200 --compare scratch_ref.npz      # on the B200
+    python tools/link_trace.py --impl reference --golden tests/golden/ref_link.npz   # compact fixture of the default size
+                                                                                     # (tests/test_gpu_link.py)
 """
 import argparse
 import os
@@ -109,11 +111,18 @@ def main():
     ap.add_argument("--channels", type=int, default=11)
     ap.add_argument("--out")
     ap.add_argument("--compare")
+    ap.add_argument("--golden", help="write the compact test fixture: 2-SpS stages, symbols, metrics and every 16th fiber sample")
     a = ap.parse_args()
     out = run(load_api(a.impl), a.symbols, a.spans, a.channels)
     print({k: (v.tolist() if v.size <= 2 else v.shape) for k, v in out.items()})
     if a.out:
         np.savez_compressed(a.out, **{k: (v.astype(np.complex64) if np.iscomplexobj(v) else v) for k, v in out.items()})
+    if a.golden:
+        keep = {k: out[k] for k in ("decimated", "edc", "ref_symbols", "equalized", "cpr", "ber", "ser", "snr")}
+        keep["fiber_every16"] = out["fiber"][::16]
+        keep["tx_every16"] = out["tx"][::16]
+        keep["geometry"] = np.array([a.symbols, a.spans, a.channels])
+        np.savez_compressed(a.golden, **{k: (v.astype(np.complex64) if np.iscomplexobj(v) else v) for k, v in keep.items()})
     if a.compare:
         with np.load(a.compare) as z:
             for k in z.files:
