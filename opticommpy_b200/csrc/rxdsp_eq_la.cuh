@@ -169,11 +169,15 @@ k_mimo_eq_la(const float2* __restrict__ X, const float2* __restrict__ REF, float
         for (int n = 0; n < NM; ++n)
 #pragma unroll
             for (int j = 0; j < TPL; ++j) {
-                const float2 pr = cmul(H[n][j], w[n][j]);  // equalization.py:464-468 (plain dot)
-                a.x += pr.x; a.y += pr.y;
+                // products accumulated inside the FMA chain (one instruction per real product instead of multiply + add:
+                // a lone warp issues in order, so the instruction count per symbol is the time)
+                const float2 h = H[n][j], xw = w[n][j];  // equalization.py:464-468 (plain dot)
+                a.x = fmaf(h.x, xw.x, fmaf(-h.y, xw.y, a.x));
+                a.y = fmaf(h.x, xw.y, fmaf(h.y, xw.x, a.y));
                 if (WL) {
-                    const float2 qq = cmul_conj(HW[n][j], w[n][j]);  // H_ . conj(x), :469-471
-                    a.x += qq.x; a.y += qq.y;
+                    const float2 hw = HW[n][j];  // H_ . conj(x), :469-471
+                    a.x = fmaf(hw.x, xw.x, fmaf(hw.y, xw.y, a.x));
+                    a.y = fmaf(hw.y, xw.x, fmaf(-hw.x, xw.y, a.y));
                 }
             }
 #pragma unroll
@@ -220,11 +224,12 @@ k_mimo_eq_la(const float2* __restrict__ X, const float2* __restrict__ REF, float
                     if constexpr (ALG == OCB_ALG_NLMS) { wg.x *= invprev[n]; wg.y *= invprev[n]; }  // :563
 #pragma unroll
                     for (int j = 0; j < TPL; ++j) {
-                        const float2 u = cmul_conj(wg, xp[n][j]);
-                        H[n][j].x += u.x; H[n][j].y += u.y;
+                        const float2 xv = xp[n][j];  // H += wg conj(x), H_ += wg x, accumulated inside the FMA chains
+                        H[n][j].x = fmaf(wg.x, xv.x, fmaf(wg.y, xv.y, H[n][j].x));
+                        H[n][j].y = fmaf(wg.y, xv.x, fmaf(-wg.x, xv.y, H[n][j].y));
                         if (WL) {
-                            const float2 vv = cmul(wg, xp[n][j]);
-                            HW[n][j].x += vv.x; HW[n][j].y += vv.y;
+                            HW[n][j].x = fmaf(wg.x, xv.x, fmaf(-wg.y, xv.y, HW[n][j].x));
+                            HW[n][j].y = fmaf(wg.x, xv.y, fmaf(wg.y, xv.x, HW[n][j].y));
                         }
                     }
                 }
