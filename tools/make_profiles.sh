@@ -22,3 +22,13 @@ for f in r2_full_ssfm r2_full_ssfm_tma r2_full_rx; do
   cat $OUT/$f.summary.txt
   rm -f $OUT/$f.ncu-rep   # gpurun brings back at most 64 MiB: the raw metric table is what gets committed
 done
+# (5) second session: warm-L2 DRAM traffic of the step loop (single pass, caches left alone), units-in-flight sweep,
+#     transmitter kernels
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --cache-control none --clock-control none \
+    -k regex:"k_time|k_freq" -s 100 -c 40 --csv --log-file $OUT/r2_inloop_traffic.csv python tools/prof_ssfm.py --steps 40 > $OUT/r2_inloop_traffic.log 2>&1
+python tools/unit_concurrency.py 16 2>&1 | tail -8 | tee $OUT/r2_unit_concurrency.jsonl
+ncu --set full --clock-control none -k regex:"k_wdm_combine|k_iqm_power|k_row_absmax2|k_upsample" -s 4 -c 4 -o $OUT/r2_full_tx \
+    python tools/prof_tx.py > $OUT/r2_full_tx.log 2>&1
+ncu -i $OUT/r2_full_tx.ncu-rep --page raw --csv > $OUT/r2_full_tx.raw.csv 2>/dev/null
+python tools/ncu_summary.py $OUT/r2_full_tx.raw.csv > $OUT/r2_full_tx.summary.txt
+rm -f $OUT/r2_full_tx.ncu-rep
