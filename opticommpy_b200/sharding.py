@@ -197,7 +197,10 @@ def run_sharded(fn, units, *args, in_flight: int = 1, **kwargs):
     that many of the rank's units in flight on its GPU (``run_concurrent``); 1 runs them one after the other."""
     mine = shard_units(len(units))
     if in_flight > 1 and len(mine) > 1:
-        local = run_concurrent(lambda i: fn(units[i], *args, **kwargs), mine, in_flight)
+        import torch
+
+        # the scheduler is the same on a CPU-only rank (gloo tests of the host logic): plain host threads, no streams
+        local = run_concurrent(lambda i: fn(units[i], *args, **kwargs), mine, in_flight, cuda=torch.cuda.is_available())
     else:
         local = {i: fn(units[i], *args, **kwargs) for i in mine}
     return gather_results(local, len(units))

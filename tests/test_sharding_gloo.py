@@ -30,11 +30,8 @@ def _worker(rank, world, port, n_units, q):
 
     rng = np.random.default_rng(0)
     units = [(rng.normal(size=(256, 2)) + 1j * rng.normal(size=(256, 2))) * 0.03 for _ in range(n_units)]
-    cfg = fo.FiberConfig(Fs=64e9, Ltotal=20, Lspan=20, hz=5.0, amp="edfa", nlprMethod=False)
-
-    def work(x, seed):
-        cfg.seed = seed
-        return fo.manakov(x, cfg)
+    def work(x, seed):  # a private config per call: units may run on concurrent host threads below
+        return fo.manakov(x, fo.FiberConfig(Fs=64e9, Ltotal=20, Lspan=20, hz=5.0, amp="edfa", nlprMethod=False, seed=seed))
 
     mine = sharding.shard_units(n_units)
     local = {i: work(units[i], 100 + i) for i in mine}
@@ -45,6 +42,9 @@ def _worker(rank, world, port, n_units, q):
     tl = {i: torch.from_numpy(local[i].astype(np.complex64)) for i in mine}
     tfull = sharding.gather_device(tl, n_units)
     ok = ok and len(tfull) == n_units and all(np.array_equal(t.numpy(), r.astype(np.complex64)) for t, r in zip(tfull, ref))
+    # run_sharded with two of the rank's units in flight (host threads on this CPU box) gives the same gathered list
+    full2 = sharding.run_sharded(lambda iu: work(units[iu], 100 + iu), list(range(n_units)), in_flight=2)
+    ok = ok and len(full2) == n_units and all(np.array_equal(a, b) for a, b in zip(full2, ref))
     sc = {i: torch.tensor([float(i), 2.0 * i, -1.0], dtype=torch.float64) for i in mine}   # three scalars per unit (cfg5)
     sfull = sharding.gather_device(sc, n_units)
     ok = ok and all(s.tolist() == [float(i), 2.0 * i, -1.0] for i, s in enumerate(sfull))
