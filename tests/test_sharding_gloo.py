@@ -164,3 +164,14 @@ def test_run_concurrent_scheduler_on_host_threads():
     import pytest
     with pytest.raises(KeyError):
         run_concurrent(bad, range(8), workers=2, cuda=False)
+
+
+def test_balanced_workers():
+    """Fewest workers (<= 8) that finish n equal units in the minimal number of rounds."""
+    from opticommpy_b200.sharding import balanced_workers
+    assert [balanced_workers(n) for n in (0, 1, 2, 8, 9, 11, 16, 17, 64)] == [1, 1, 2, 8, 5, 6, 8, 6, 8]
+    for n in range(1, 200):
+        w = balanced_workers(n)
+        assert 1 <= w <= 8 and -(-n // w) == -(-n // 8)       # never more rounds than with 8 workers
+        assert w == 1 or -(-n // (w - 1)) > -(-n // 8)          # and no smaller pool achieves that
+    assert balanced_workers(11, max_workers=4) == 4 and balanced_workers(5, max_workers=2) == 2
